@@ -105,7 +105,7 @@ SYMBOLS = {
     'os2r_set_state': (_i32, [_vp, _vp]),
     'os2r_get_params': (_i32, [_vp, _vp]),
     'os2r_set_params': (_i32, [_vp, _vp]),
-    'os2r_get_episode': (_i32, [_vp, _vp, _vp]),
+    'os2r_get_episode': (_i32, [_vp, _vp, _vp, _vp]),
     'os2r_stats_read': (_i32, [_vp, C.POINTER(Stats), _i32]),
     'os2r_num_envs': (C.c_int64, [_vp]),
     'os2r_obs_dim': (_i32, [_vp]),

@@ -1,0 +1,120 @@
+"""VecEnv facade over one batched ``CudaRuntime`` — API of gym_os2r/common/vec_env/vec_env.py:32-245
+and subproc_vec_env.py:52-229 (``reset`` / ``step_async`` / ``step_wait`` / ``step`` /
+``get_state_info`` / ``seed`` / ``close`` / ``get_attr`` / ``set_attr`` / ``env_method``).
+
+``step_async`` enqueues the fused kernel on the current CUDA stream, ``step_wait`` synchronises and
+hands back the results. ``output='numpy'`` (default, what reference scripts expect) returns host
+arrays ``(obs[N,D] float32, rew[N], done[N] bool, infos)``; ``output='torch'`` keeps everything on the
+device for a GPU-resident training loop. Auto-reset semantics follow the reference worker
+(subproc_vec_env.py:14-21): on done the returned observation is the reset observation and the
+terminal one is in ``infos``; reward/done are those of the terminal step."""
+from collections.abc import Sequence
+
+import numpy as np
+import torch
+
+
+class LazyInfos(Sequence):
+    """The per-env ``info`` dicts of a step, built on access: materialising 65 536 dicts per step
+    would cost more than the physics. ``infos[i]`` / iteration / ``len`` behave like the reference's tuple."""
+
+    def __init__(self, names, reset_ids, done, terminal_obs, truncated):
+        self._names, self._rid, self._done, self._term, self._trunc = names, reset_ids, done, terminal_obs, truncated
+
+    def __len__(self):
+        return len(self._rid)
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [self[j] for j in range(*i.indices(len(self)))]
+        if i < 0:
+            i += len(self)
+        d = {'reset_orientation': self._names[int(self._rid[i])]}
+        if self._done[i]:
+            if self._term is not None:
+                d['terminal_observation'] = self._term[i]
+            if self._trunc[i]:
+                d['TimeLimit.truncated'] = True
+        return d
+
+
+class CudaVecEnv:
+    def __init__(self, env, output: str = 'numpy'):
+        assert output in ('numpy', 'torch')
+        self.env = env
+        self.runtime = env.unwrapped
+        self.num_envs = self.runtime.num_envs
+        self.observation_space = env.observation_space
+        self.action_space = env.action_space
+        self.output = output
+        self.waiting = False
+        self.closed = False
+        self._pending = None
+
+    def _out(self, t):
+        return t.detach().cpu().numpy() if self.output == 'numpy' else t
+
+    def reset(self):
+        obs = self.env.reset()
+        if self.output == 'numpy':
+            torch.cuda.synchronize()
+        return self._out(obs)
+
+    def step_async(self, actions):
+        custom = self.runtime._cfg.reward_id == 0
+        if self.output == 'numpy' and not custom:
+            self._pending = ('host', np.asarray(actions, dtype=np.float32))   # runs in step_wait (synchronous API)
+        else:
+            self._pending = ('device', self.env.step(actions))                # enqueued on the current stream
+        self.waiting = True
+
+    def step_wait(self):
+        kind, payload = self._pending
+        self._pending, self.waiting = None, False
+        names = self.runtime.task.reset_positions
+        if kind == 'host':
+            # numpy in / numpy out through the C-ABI host entry point (pinned staging, H2D + kernel + D2H)
+            obs, rew, done, term, info = self.runtime.engine.step_host(payload, want_terminal_obs=True, want_info=True)
+            return obs, rew, done, LazyInfos(names, info[:, 0], done, term, (info[:, 1] & 3) == 2)
+        obs, rew, done, info = payload
+        if self.output == 'torch':
+            return obs, rew, done, info
+        torch.cuda.synchronize()
+        done_h = done.cpu().numpy()
+        rid = info['reset_orientation'].cpu().numpy()
+        term = info['terminal_observation'].cpu().numpy() if done_h.any() else None
+        trunc = info['TimeLimit.truncated'].cpu().numpy()
+        return obs.cpu().numpy(), rew.cpu().numpy(), done_h, LazyInfos(names, rid, done_h, term, trunc)
+
+    def step(self, actions):
+        self.step_async(actions)
+        return self.step_wait()
+
+    def get_state_info(self, states, actions):
+        rew, done = self.runtime.task.get_state_info(states, actions)
+        return (self._out(rew) if torch.is_tensor(rew) else np.asarray(rew),
+                self._out(done) if torch.is_tensor(done) else np.asarray(done))
+
+    def seed(self, seed=None):
+        return self.env.seed(seed)
+
+    def render(self, mode='human'):
+        return self.env.render(mode)
+
+    def close(self):
+        if not self.closed:
+            self.env.close()
+            self.closed = True
+
+    def get_attr(self, attr_name, indices=None):
+        return [getattr(self.env, attr_name)]
+
+    def set_attr(self, attr_name, value, indices=None):
+        setattr(self.runtime, attr_name, value)
+
+    def env_method(self, method_name, *args, indices=None, **kwargs):
+        return [getattr(self.env, method_name)(*args, **kwargs)]
+
+    @property
+    def unwrapped(self):
+        return self.runtime

@@ -1,0 +1,720 @@
+// os2r_device.cuh — device-side monopod physics + task epilogue for sm_100a.
+//
+// One thread steps one environment through `substeps` physics iterations and the fused task
+// epilogue (observation, reward, termination, auto-reset, randomiser draws). All model constants
+// arrive as a __grid_constant__ kernel parameter (constant bank, broadcast to the warp); per-env
+// state lives in HBM as structure-of-arrays [field][env] so every load/store is coalesced.
+//
+// Formulation (deliberately different from the CPU oracle's body-frame ABA):
+//   * every joint is normalised on the host to rotate about its child-frame x axis;
+//   * one forward-kinematics pass gives world-aligned joint axes a_i, joint origins, COM offsets,
+//     rotated inertias and contact-sphere centres; all spatial quantities are then expressed in
+//     world-aligned axes about a reference point O at the knee joint (keeps |r| small for the light
+//     leg links so fp32 cancellation in m*|r|^2 terms stays benign);
+//   * mass matrix by the composite-rigid-body method, bias forces by recursive Newton-Euler, both
+//     in that single frame (no per-body spatial transforms);
+//   * qdd from a Cholesky solve of (M + dt*D) (implicit joint damping, as DART);
+//   * constraints (Coulomb joint friction rows + per-contact normal / 2 friction rows) solved by
+//     projected Gauss-Seidel in Cholesky-whitened velocity coordinates z = L^T v: each row needs a
+//     single n-vector G_r = L^-1 J_r^T (row velocity = G_r.z, update z += G_r*dlambda,
+//     A_rr = |G_r|^2), which halves the register footprint versus storing J_r and M^-1 J_r^T;
+//   * positions are integrated with a compensated (hi, lo) float pair in the fp32 build.
+//
+// Reference semantics restated: gym_os2r/runtimes/gazebo_runtime.py:65-97 (10x zero-order hold),
+// gym_os2r/tasks/monopod.py:202-298 (torque map, observation, done), gym_os2r/rewards/,
+// gym_os2r/randomizers/monopod.py:56-135,182-215, gym_os2r/utils/reset.py.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/os2r.h"
+
+namespace os2r {
+
+// ------------------------------------------------------------------------------------------------
+// device-side constant tables
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+struct ModelDev {
+    T tree_R[OS2R_MAX_DOF][9];   // row-major, joint axis already normalised to child x
+    T tree_p[OS2R_MAX_DOF][3];
+    T mass[OS2R_MAX_DOF];
+    T com[OS2R_MAX_DOF][3];
+    T inertia[OS2R_MAX_DOF][6];  // xx yy zz xy xz yz
+    T contact_pos[OS2R_MAX_CONTACTS][3];
+    T contact_radius[OS2R_MAX_CONTACTS];
+    T dt, erp_over_dt, max_erv, cfm_contact, cfm_joint;
+    T max_torque[2];
+    int32_t contact_body[OS2R_MAX_CONTACTS];
+    int32_t hip_dof, knee_dof;
+    int32_t substeps, pgs_iters;
+    int32_t any_damping;         // 0 when every joint's nominal damping is 0 (skip 2nd factorisation)
+};
+
+struct TaskDev {                 // epilogue + reset configuration (fp64: evaluated once per env step)
+    os2r_task_cfg cfg;
+    double nominal_damping[OS2R_MAX_DOF];
+    double nominal_friction[OS2R_MAX_DOF];
+    double nominal_mu[OS2R_MAX_CONTACTS];
+    int32_t role_dof[OS2R_N_ROLES];
+    int32_t n_dof, n_contacts;
+};
+
+// SoA views of the per-env state in HBM. Every array is [count][n_envs].
+template <typename T>
+struct StateDev {
+    T *q_hi, *q_lo, *qd;         // [n_dof][N]
+    T *lam;                      // [rows][N]   warm-start impulses
+    T *a_prev;                   // [2][N]      last applied action
+    T *mass_scale, *damping, *friction;  // [n_dof][N]
+    T *mu;                       // [n_contacts][N]
+    T *gravity_z;                // [N]
+    int32_t *steps;              // [N] steps in the current episode
+    uint32_t *episode;           // [N] episode counter (RNG counter word)
+    int32_t *reset_id;           // [N]
+    double *ret;                 // [N] return of the current episode
+    int64_t n_envs;
+    int64_t first_env_id;
+    uint64_t seed;
+};
+
+struct StatsDev {                // device-side accumulators (os2r_stats without env_steps)
+    unsigned long long episodes, done_task, done_timelimit, nonfinite_resets;
+    double sum_return, sum_length;
+};
+
+// ------------------------------------------------------------------------------------------------
+// scalar helpers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void sincos_t(float x, float *s, float *c) { sincosf(x, s, c); }
+__device__ __forceinline__ void sincos_t(double x, double *s, double *c) { sincos(x, s, c); }
+__device__ __forceinline__ float sqrt_t(float x) { return sqrtf(x); }
+__device__ __forceinline__ double sqrt_t(double x) { return sqrt(x); }
+__device__ __forceinline__ float rcp_t(float x) { return 1.0f / x; }
+__device__ __forceinline__ double rcp_t(double x) { return 1.0 / x; }
+__device__ __forceinline__ float fmin_t(float a, float b) { return fminf(a, b); }
+__device__ __forceinline__ double fmin_t(double a, double b) { return fmin(a, b); }
+__device__ __forceinline__ float fmax_t(float a, float b) { return fmaxf(a, b); }
+__device__ __forceinline__ double fmax_t(double a, double b) { return fmax(a, b); }
+
+#define OS2R_CROSS(o, a, b)                    \
+    do {                                       \
+        (o)[0] = (a)[1] * (b)[2] - (a)[2] * (b)[1]; \
+        (o)[1] = (a)[2] * (b)[0] - (a)[0] * (b)[2]; \
+        (o)[2] = (a)[0] * (b)[1] - (a)[1] * (b)[0]; \
+    } while (0)
+#define OS2R_CROSS_ACC(o, a, b)                 \
+    do {                                        \
+        (o)[0] += (a)[1] * (b)[2] - (a)[2] * (b)[1]; \
+        (o)[1] += (a)[2] * (b)[0] - (a)[0] * (b)[2]; \
+        (o)[2] += (a)[0] * (b)[1] - (a)[1] * (b)[0]; \
+    } while (0)
+#define OS2R_DOT(a, b) ((a)[0] * (b)[0] + (a)[1] * (b)[1] + (a)[2] * (b)[2])
+
+// symmetric 3x3 (xx yy zz xy xz yz) times vector
+#define OS2R_SYMV(o, S, v)                                        \
+    do {                                                          \
+        (o)[0] = (S)[0] * (v)[0] + (S)[3] * (v)[1] + (S)[4] * (v)[2]; \
+        (o)[1] = (S)[3] * (v)[0] + (S)[1] * (v)[1] + (S)[5] * (v)[2]; \
+        (o)[2] = (S)[4] * (v)[0] + (S)[5] * (v)[1] + (S)[2] * (v)[2]; \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// Philox4x32-10, identical stream layout to the oracle (key = seed, counter = env, episode, block)
+// ------------------------------------------------------------------------------------------------
+__device__ inline void philox4x32(uint64_t seed, uint64_t env_id, uint32_t episode, uint32_t block, uint32_t out[4]) {
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    uint32_t c0 = (uint32_t)env_id, c1 = (uint32_t)(env_id >> 32), c2 = episode, c3 = block;
+#pragma unroll 1
+    for (int r = 0; r < 10; ++r) {
+        uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+__device__ inline double rng_uniform(uint64_t seed, uint64_t env_id, uint32_t episode, uint32_t k) {
+    uint32_t x[4];
+    philox4x32(seed, env_id, episode, k >> 1, x);
+    uint32_t a = (k & 1) ? x[2] : x[0], b = (k & 1) ? x[3] : x[1];
+    return ((double)(a >> 5) * 67108864.0 + (double)(b >> 6)) * (1.0 / 9007199254740992.0);
+}
+__device__ inline void rng_normal2(uint64_t seed, uint64_t env_id, uint32_t episode, uint32_t k, double z[2]) {
+    double u1 = rng_uniform(seed, env_id, episode, k), u2 = rng_uniform(seed, env_id, episode, k + 1);
+    double r = sqrt(-2.0 * log(1.0 - u1));
+    double s, c;
+    sincos(6.283185307179586476925 * u2, &s, &c);
+    z[0] = r * c; z[1] = r * s;
+}
+enum { DRAW_RESET = 0, DRAW_PITCH = 1, DRAW_NOISE = 2, DRAW_LAYSIDE = 4, DRAW_DIR = 5, DRAW_YAW = 6,
+       DRAW_SIMPLE_HIP = 7, DRAW_SIMPLE_KNEE = 8, DRAW_PARAMS = 10 };
+#define OS2R_EPISODE_GRAVITY 0xFFFFFFFFu
+
+// ------------------------------------------------------------------------------------------------
+// one physics iteration
+// ------------------------------------------------------------------------------------------------
+template <typename T, int N, int NC>
+struct EnvRegs {                 // per-thread working set that persists across physics iterations
+    T q_hi[N], q_lo[N], v[N];
+    T lam[N + 3 * NC];
+    T mass_scale[N], damping[N], fric_dt[N];   // fric_dt = friction * dt (impulse bound)
+    T mu[NC];
+    T gz;                        // gravity z (negative)
+    T tau[N];
+};
+
+template <typename T, int N, int NC>
+__device__ __forceinline__ void physics_iteration(const ModelDev<T> &M, EnvRegs<T, N, NC> &E) {
+    constexpr int ROWS = N + 3 * NC;
+    const T dt = M.dt;
+
+    // ---- forward kinematics (world-aligned), everything relative to the body's joint origin ----
+    T ax[N][3];      // joint axis, world
+    T P[N][3];       // joint origin, world (absolute until O is known)
+    T dcom[N][3];    // COM offset from the joint origin, world axes
+    T Iw[N][6];      // rotational inertia about the COM, world axes
+    T cx[NC][3];     // contact sphere centres, world (absolute)
+    {
+        T R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+        T p[3] = {0, 0, 0};
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            T A[9];
+            if (i == 0) {
+#pragma unroll
+                for (int k = 0; k < 3; ++k) p[k] = M.tree_p[0][k];
+#pragma unroll
+                for (int k = 0; k < 9; ++k) A[k] = M.tree_R[0][k];
+            } else {
+                const T *tp = M.tree_p[i];
+#pragma unroll
+                for (int r = 0; r < 3; ++r) p[r] += R[3 * r] * tp[0] + R[3 * r + 1] * tp[1] + R[3 * r + 2] * tp[2];
+                const T *tR = M.tree_R[i];
+#pragma unroll
+                for (int r = 0; r < 3; ++r)
+#pragma unroll
+                    for (int c = 0; c < 3; ++c)
+                        A[3 * r + c] = R[3 * r] * tR[c] + R[3 * r + 1] * tR[3 + c] + R[3 * r + 2] * tR[6 + c];
+            }
+            T s, c;
+            sincos_t(E.q_hi[i], &s, &c);
+            if (sizeof(T) == 4) {   // compensated position: sin(hi+lo) = s + lo*c, cos(hi+lo) = c - lo*s
+                T s2 = s + E.q_lo[i] * c;
+                c = c - E.q_lo[i] * s;
+                s = s2;
+            }
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                T a1 = A[3 * r + 1], a2 = A[3 * r + 2];
+                R[3 * r] = A[3 * r];
+                R[3 * r + 1] = c * a1 + s * a2;
+                R[3 * r + 2] = c * a2 - s * a1;
+                ax[i][r] = A[3 * r];
+                P[i][r] = p[r];
+            }
+            const T *cm = M.com[i];
+#pragma unroll
+            for (int r = 0; r < 3; ++r) dcom[i][r] = R[3 * r] * cm[0] + R[3 * r + 1] * cm[1] + R[3 * r + 2] * cm[2];
+            {   // Iw = R * Ibody * R^T (symmetric)
+                const T *Ib = M.inertia[i];
+                T t[9];
+#pragma unroll
+                for (int r = 0; r < 3; ++r) {
+                    t[3 * r + 0] = R[3 * r] * Ib[0] + R[3 * r + 1] * Ib[3] + R[3 * r + 2] * Ib[4];
+                    t[3 * r + 1] = R[3 * r] * Ib[3] + R[3 * r + 1] * Ib[1] + R[3 * r + 2] * Ib[5];
+                    t[3 * r + 2] = R[3 * r] * Ib[4] + R[3 * r + 1] * Ib[5] + R[3 * r + 2] * Ib[2];
+                }
+                Iw[i][0] = t[0] * R[0] + t[1] * R[1] + t[2] * R[2];
+                Iw[i][1] = t[3] * R[3] + t[4] * R[4] + t[5] * R[5];
+                Iw[i][2] = t[6] * R[6] + t[7] * R[7] + t[8] * R[8];
+                Iw[i][3] = t[0] * R[3] + t[1] * R[4] + t[2] * R[5];
+                Iw[i][4] = t[0] * R[6] + t[1] * R[7] + t[2] * R[8];
+                Iw[i][5] = t[3] * R[6] + t[4] * R[7] + t[5] * R[8];
+            }
+#pragma unroll
+            for (int k = 0; k < NC; ++k) {
+                if (M.contact_body[k] == i) {
+                    const T *cp = M.contact_pos[k];
+#pragma unroll
+                    for (int r = 0; r < 3; ++r) cx[k][r] = p[r] + R[3 * r] * cp[0] + R[3 * r + 1] * cp[1] + R[3 * r + 2] * cp[2];
+                }
+            }
+        }
+    }
+    // reference point O = origin of the LAST joint (knee): its motion vector has no linear part, so the
+    // lightest, most torque-sensitive row of M and of the bias is formed without m*|r|^2 cancellation
+    constexpr int IO = N - 1;
+    const T Ox = P[IO][0], Oy = P[IO][1], Oz = P[IO][2];
+    T lin[N][3];     // linear part of the joint motion vector: velocity of the point at O per unit rate
+    T cO[N][3];      // COM relative to O
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        T rho[3] = {P[i][0] - Ox, P[i][1] - Oy, P[i][2] - Oz};
+        OS2R_CROSS(lin[i], rho, ax[i]);
+#pragma unroll
+        for (int r = 0; r < 3; ++r) cO[i][r] = rho[r] + dcom[i][r];
+    }
+
+    // ---- recursive Newton-Euler bias (qdd = 0) + per-body spatial inertia about O --------------
+    T Fn[N][3], Ff[N][3];      // body net wrench (moment about O, force)
+    T bm[N], bh[N][3], bI[N][6];
+    {
+        T w[3] = {0, 0, 0}, vO[3] = {0, 0, 0}, al[3] = {0, 0, 0}, ac[3] = {0, 0, -E.gz};
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            const T qd = E.v[i];
+            if (i > 0) {   // sdot = [w x a ; w x lin + vO x a]  (parent twist)
+                T sa[3], sl[3];
+                OS2R_CROSS(sa, w, ax[i]);
+                OS2R_CROSS(sl, w, lin[i]);
+                OS2R_CROSS_ACC(sl, vO, ax[i]);
+#pragma unroll
+                for (int r = 0; r < 3; ++r) { al[r] += sa[r] * qd; ac[r] += sl[r] * qd; }
+            }
+#pragma unroll
+            for (int r = 0; r < 3; ++r) { w[r] += ax[i][r] * qd; vO[r] += lin[i][r] * qd; }
+            const T m = M.mass[i] * E.mass_scale[i];
+            const T *c = cO[i];
+            bm[i] = m;
+#pragma unroll
+            for (int r = 0; r < 3; ++r) bh[i][r] = m * c[r];
+            const T cc = OS2R_DOT(c, c);
+            bI[i][0] = Iw[i][0] + m * (cc - c[0] * c[0]);
+            bI[i][1] = Iw[i][1] + m * (cc - c[1] * c[1]);
+            bI[i][2] = Iw[i][2] + m * (cc - c[2] * c[2]);
+            bI[i][3] = Iw[i][3] - m * c[0] * c[1];
+            bI[i][4] = Iw[i][4] - m * c[0] * c[2];
+            bI[i][5] = Iw[i][5] - m * c[1] * c[2];
+            // momentum: Nn = I w + h x vO ; Pp = m vO - h x w
+            T Nn[3], Pp[3], t3[3];
+            OS2R_SYMV(Nn, bI[i], w);
+            OS2R_CROSS_ACC(Nn, bh[i], vO);
+            OS2R_CROSS(t3, bh[i], w);
+#pragma unroll
+            for (int r = 0; r < 3; ++r) Pp[r] = m * vO[r] - t3[r];
+            // wrench: Fn = I al + h x ac + w x Nn + vO x Pp ; Ff = m ac - h x al + w x Pp
+            OS2R_SYMV(Fn[i], bI[i], al);
+            OS2R_CROSS_ACC(Fn[i], bh[i], ac);
+            OS2R_CROSS_ACC(Fn[i], w, Nn);
+            OS2R_CROSS_ACC(Fn[i], vO, Pp);
+            OS2R_CROSS(t3, bh[i], al);
+#pragma unroll
+            for (int r = 0; r < 3; ++r) Ff[i][r] = m * ac[r] - t3[r];
+            OS2R_CROSS_ACC(Ff[i], w, Pp);
+        }
+    }
+    // ---- backward pass: bias forces and composite-rigid-body mass matrix ------------------------
+    T Mm[N][N];      // lower triangle used (Mm[i][j], j <= i)
+    T rhs[N];
+    {
+        T cn[3] = {0, 0, 0}, cf[3] = {0, 0, 0};
+        T Cm = 0, Ch[3] = {0, 0, 0}, CI[6] = {0, 0, 0, 0, 0, 0};
+#pragma unroll
+        for (int i = N - 1; i >= 0; --i) {
+#pragma unroll
+            for (int r = 0; r < 3; ++r) { cn[r] += Fn[i][r]; cf[r] += Ff[i][r]; Ch[r] += bh[i][r]; }
+#pragma unroll
+            for (int r = 0; r < 6; ++r) CI[r] += bI[i][r];
+            Cm += bm[i];
+            const T bias = OS2R_DOT(ax[i], cn) + OS2R_DOT(lin[i], cf);
+            rhs[i] = E.tau[i] - E.damping[i] * E.v[i] - bias;
+            // f = Ic * s_i
+            T fn[3], ff[3], t3[3];
+            OS2R_SYMV(fn, CI, ax[i]);
+            OS2R_CROSS_ACC(fn, Ch, lin[i]);
+            OS2R_CROSS(t3, Ch, ax[i]);
+#pragma unroll
+            for (int r = 0; r < 3; ++r) ff[r] = Cm * lin[i][r] - t3[r];
+#pragma unroll
+            for (int j = 0; j <= i; ++j) Mm[i][j] = OS2R_DOT(ax[j], fn) + OS2R_DOT(lin[j], ff);
+        }
+    }
+    // ---- qdd from (M + dt*D) by Cholesky, v* = v + dt*qdd ------------------------------------------
+    T L[N][N];       // Cholesky factor of the plain M (lower), diagonal stored as reciprocal in Ld
+    T Ld[N];
+    T vs[N];
+    auto cholesky = [&](const T *dadd, T(&Lo)[N][N], T(&Lrd)[N]) {
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+            T d = Mm[j][j] + dadd[j];
+#pragma unroll
+            for (int k = 0; k < j; ++k) d -= Lo[j][k] * Lo[j][k];
+            const T sd = sqrt_t(d);
+            const T rd = rcp_t(sd);
+            Lo[j][j] = sd;
+            Lrd[j] = rd;
+#pragma unroll
+            for (int i = j + 1; i < N; ++i) {
+                T s = Mm[i][j];
+#pragma unroll
+                for (int k = 0; k < j; ++k) s -= Lo[i][k] * Lo[j][k];
+                Lo[i][j] = s * rd;
+            }
+        }
+    };
+    auto solve = [&](const T(&Lo)[N][N], const T(&Lrd)[N], const T *b, T *x) {
+        T y[N];
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            T s = b[i];
+#pragma unroll
+            for (int k = 0; k < i; ++k) s -= Lo[i][k] * y[k];
+            y[i] = s * Lrd[i];
+        }
+#pragma unroll
+        for (int i = N - 1; i >= 0; --i) {
+            T s = y[i];
+#pragma unroll
+            for (int k = i + 1; k < N; ++k) s -= Lo[k][i] * x[k];
+            x[i] = s * Lrd[i];
+        }
+    };
+    {
+        T zero[N];
+#pragma unroll
+        for (int i = 0; i < N; ++i) zero[i] = 0;
+        cholesky(zero, L, Ld);
+        T qdd[N];
+        if (M.any_damping) {
+            T dd[N], L2[N][N], L2d[N];
+#pragma unroll
+            for (int i = 0; i < N; ++i) dd[i] = dt * E.damping[i];
+            cholesky(dd, L2, L2d);
+            solve(L2, L2d, rhs, qdd);
+        } else {
+            solve(L, Ld, rhs, qdd);
+        }
+#pragma unroll
+        for (int i = 0; i < N; ++i) vs[i] = E.v[i] + dt * qdd[i];
+    }
+    // whitened velocity z0 = L^T v*. The solver tracks only the impulse-induced change dz (z = z0 + dz):
+    // v_new = v* + L^-T dz, so the (usually tiny) constraint correction never round-trips v through L.
+    T z0[N], z[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        T s = 0;
+#pragma unroll
+        for (int k = i; k < N; ++k) s += L[k][i] * vs[k];
+        z0[i] = s;
+        z[i] = 0;
+    }
+    // ---- constraint rows -----------------------------------------------------------------------------
+    // joint friction row r: G = column r of L^-1 (entries k >= r)
+    T Gj[N][N];      // Gj[r][k], k >= r
+    T Aj[N], bj[N];
+#pragma unroll
+    for (int r = 0; r < N; ++r) {
+        T a = 0;
+#pragma unroll
+        for (int k = r; k < N; ++k) {
+            T s = (k == r) ? T(1) : T(0);
+#pragma unroll
+            for (int m = r; m < k; ++m) s -= L[k][m] * Gj[r][m];
+            Gj[r][k] = s * Ld[k];
+            a += Gj[r][k] * Gj[r][k];
+        }
+        Aj[r] = rcp_t(a * (T(1) + M.cfm_joint));   // reciprocal of the regularised diagonal
+        T b = 0;
+#pragma unroll
+        for (int k = r; k < N; ++k) b += Gj[r][k] * z0[k];
+        bj[r] = b;                                  // row velocity before any impulse
+    }
+    // contact rows
+    T Gc[NC][3][N];
+    T Ac[NC][3];
+    T bc[NC][3];     // row velocity before any impulse, minus the target (penetration correction)
+    bool act[NC];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+        const T depth = M.contact_radius[c] - cx[c][2];
+        act[c] = depth > T(0);
+        if (act[c]) {
+            const T bounce = fmin_t(depth * M.erp_over_dt, M.max_erv);
+            const T x[3] = {cx[c][0] - Ox, cx[c][1] - Oy, cx[c][2] - M.contact_radius[c] - Oz};
+            T J[3][N];   // rows: normal (z), tangent x, tangent y
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                T jc[3];
+                OS2R_CROSS(jc, ax[i], x);
+                const bool on = i <= M.contact_body[c];
+                J[0][i] = on ? jc[2] + lin[i][2] : T(0);
+                J[1][i] = on ? jc[0] + lin[i][0] : T(0);
+                J[2][i] = on ? jc[1] + lin[i][1] : T(0);
+            }
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+                T a = 0, b = (d == 0) ? -bounce : T(0);
+#pragma unroll
+                for (int k = 0; k < N; ++k) {
+                    T s = J[d][k];
+#pragma unroll
+                    for (int m = 0; m < k; ++m) s -= L[k][m] * Gc[c][d][m];
+                    Gc[c][d][k] = s * Ld[k];
+                    a += Gc[c][d][k] * Gc[c][d][k];
+                    b += Gc[c][d][k] * z0[k];
+                }
+                Ac[c][d] = rcp_t(a * (T(1) + M.cfm_contact));
+                bc[c][d] = b;
+            }
+        } else {
+#pragma unroll
+            for (int d = 0; d < 3; ++d) E.lam[N + 3 * c + d] = 0;
+        }
+    }
+    // ---- warm start ------------------------------------------------------------------------------------
+#pragma unroll
+    for (int r = 0; r < N; ++r) {
+        if (E.fric_dt[r] > T(0)) {
+#pragma unroll
+            for (int k = r; k < N; ++k) z[k] += Gj[r][k] * E.lam[r];
+        } else E.lam[r] = 0;
+    }
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+        if (act[c]) {
+#pragma unroll
+            for (int d = 0; d < 3; ++d)
+#pragma unroll
+                for (int k = 0; k < N; ++k) z[k] += Gc[c][d][k] * E.lam[N + 3 * c + d];
+        }
+    }
+    // ---- projected Gauss-Seidel sweeps in z-space ------------------------------------------------------
+    // Row update with relative CFM c on the diagonal A(1+c):
+    //   lam' = clamp(lam - (G.z - target + c*A*lam) / (A(1+c))) = clamp(lam*(1-k) - (G.z - target)*inv),
+    //   k = c/(1+c), inv = 1/(A(1+c)) precomputed per row.
+    const T kj = M.cfm_joint / (T(1) + M.cfm_joint), kc = M.cfm_contact / (T(1) + M.cfm_contact);
+#pragma unroll 1
+    for (int it = 0; it < M.pgs_iters; ++it) {
+#pragma unroll
+        for (int r = 0; r < N; ++r) {
+            if (E.fric_dt[r] > T(0)) {
+                T w = bj[r];
+#pragma unroll
+                for (int k = r; k < N; ++k) w += Gj[r][k] * z[k];
+                T nl = E.lam[r] - (kj * E.lam[r] + w * Aj[r]);
+                nl = fmax_t(-E.fric_dt[r], fmin_t(E.fric_dt[r], nl));
+                const T dl = nl - E.lam[r];
+#pragma unroll
+                for (int k = r; k < N; ++k) z[k] += Gj[r][k] * dl;
+                E.lam[r] = nl;
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+            if (act[c]) {
+#pragma unroll
+                for (int d = 0; d < 3; ++d) {
+                    const int r = N + 3 * c + d;
+                    T w = bc[c][d];
+#pragma unroll
+                    for (int k = 0; k < N; ++k) w += Gc[c][d][k] * z[k];
+                    T nl = E.lam[r] - (kc * E.lam[r] + w * Ac[c][d]);
+                    if (d == 0) nl = fmax_t(nl, T(0));
+                    else {
+                        const T lim = E.mu[c] * E.lam[N + 3 * c];
+                        nl = fmax_t(-lim, fmin_t(lim, nl));
+                    }
+                    const T dl = nl - E.lam[r];
+#pragma unroll
+                    for (int k = 0; k < N; ++k) z[k] += Gc[c][d][k] * dl;
+                    E.lam[r] = nl;
+                }
+            }
+        }
+    }
+    (void)ROWS;
+    // ---- v = v* + L^-T dz ; q += dt v (compensated in fp32) ---------------------------------------------
+    {
+        T dv[N];
+#pragma unroll
+        for (int i = N - 1; i >= 0; --i) {
+            T s = z[i];
+#pragma unroll
+            for (int k = i + 1; k < N; ++k) s -= L[k][i] * dv[k];
+            dv[i] = s * Ld[i];
+        }
+#pragma unroll
+        for (int i = 0; i < N; ++i) E.v[i] = vs[i] + dv[i];
+    }
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        if (sizeof(T) == 4) {
+            const T b = dt * E.v[i] + E.q_lo[i];
+            const T a = E.q_hi[i];
+            const T s = a + b;
+            const T bb = s - a;
+            E.q_lo[i] = (a - (s - bb)) + (b - bb);
+            E.q_hi[i] = s;
+        } else {
+            E.q_hi[i] += dt * E.v[i];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// task epilogue (fp64): observation, reward, termination — once per env step
+// ------------------------------------------------------------------------------------------------
+__device__ inline double np_mod_pos(double x, double y) {
+    double r = fmod(x, y);
+    if (r != 0.0) { if (r < 0.0) r += y; } else r = 0.0;
+    return r;
+}
+
+// raw[] (masked, wrapped) and normalised obs[]; returns done-by-task
+template <int N>
+__device__ inline bool observe(const TaskDev &K, const double *q, const double *v, const double *a_old,
+                               double *obs) {
+    const os2r_task_cfg &C = K.cfg;
+    const double PI = 3.141592653589793;
+    bool done = false;
+#pragma unroll 1
+    for (int k = 0; k < C.obs_dim; ++k) {
+        const int kind = C.obs_kind[k], idx = C.obs_index[k];
+        double x = 0;
+        // idx is runtime: select without dynamic register indexing
+        if (kind == OS2R_OBS_TORQUE) x = idx == 0 ? a_old[0] : a_old[1];
+        else {
+#pragma unroll
+            for (int i = 0; i < N; ++i)
+                if (i == idx) x = (kind == OS2R_OBS_VEL) ? v[i] : q[i];
+        }
+        if (kind == OS2R_OBS_POS_PERIODIC) x = np_mod_pos(x + PI, 2 * PI) - PI;
+        done |= !(x >= C.done_low[k]) || !(x <= C.done_high[k]);
+        double o = x;
+        if (C.normalized) {
+            if (kind == OS2R_OBS_VEL) o = tanh(0.05 * x);
+            else o = 2 * (x - C.obs_low[k]) / (C.obs_high[k] - C.obs_low[k]) - 1;
+        }
+        obs[k] = o;
+    }
+    return done;
+}
+
+__device__ inline double quad_tol(double x, double margin, double vam) {   // tolerance(x, (0,0), margin, quadratic)
+    if (x == 0.0) return 1.0;
+    const double sx = (fabs(x) / margin) * sqrt(1 - vam);
+    return fabs(sx) < 1 ? 1 - sx * sx : 0.0;
+}
+__device__ inline double lin_tol(double x, double margin, double vam) {
+    if (x == 0.0) return 1.0;
+    const double sx = (fabs(x) / margin) * (1 - vam);
+    return fabs(sx) < 1 ? 1 - sx : 0.0;
+}
+
+// rewards/__init__.py:66-207 ; a0 current action, a1 previous
+__device__ inline double reward_fn(const os2r_task_cfg &C, const double *obs, const double *a0, const double *a1) {
+    const double H = C.normalized ? 0.11 / 1.57 : 0.11;
+    double bp = 0;
+    if (C.reward_pitch_col >= 0) bp = obs[C.reward_pitch_col];
+    const double band = (H <= bp && bp <= 4 * H) ? 1.0 : 0.0;
+    switch (C.reward_id) {
+    case OS2R_REWARD_BALANCING_V1: return band;
+    case OS2R_REWARD_BALANCING_V2: return band * quad_tol(a0[0], 1, 0.4) * quad_tol(a0[1], 1, 0.4);
+    case OS2R_REWARD_BALANCING_V3: {
+        double up = 1.0;
+        if (band == 0.0) {
+            const double d = (bp < H ? H - bp : bp - 4 * H) / 0.01;
+            const double sc = sqrt(1 / 0.1 - 1);
+            up = 1 / ((d * sc) * (d * sc) + 1);
+        }
+        return up * quad_tol(a0[0] - a1[0], 1, 0.1) * quad_tol(a0[1] - a1[1], 1, 0.1); }
+    case OS2R_REWARD_HOPPING_V1: {
+        const double hv = obs[C.reward_yawvel_col];
+        double move = 1.0;
+        if (!(0.25 <= hv && hv <= 0.3)) {
+            const double d = (hv < 0.25 ? 0.25 - hv : hv - 0.3) / 0.15;
+            const double t = tanh(d * atanh(sqrt(1 - 0.1)));
+            move = 1 - t * t;
+        }
+        return band * quad_tol(a0[0] - a1[0], 0.1, 0.0) * quad_tol(a0[1] - a1[1], 0.1, 0.0) * move; }
+    case OS2R_REWARD_STRAIGHT_V1: {
+        double sc = (quad_tol(a0[0] / 20, 1, 0.0) + quad_tol(a0[1] / 20, 1, 0.0)) / 2;
+        sc = (4 + sc) / 5;
+        return lin_tol(obs[C.reward_hip_col], 1, 0.1) * lin_tol(obs[C.reward_knee_col], 1, 0.1) * sc; }
+    default: return 0.0;
+    }
+}
+
+// utils/reset.py:4-40
+__device__ inline void leg_joint_angles(const os2r_task_cfg &C, double bp, double out[2]) {
+    const double lh = (C.ik_boom * sin(bp) + C.ik_pivot_height) / cos(bp);
+    const double ul = C.ik_upper_leg, ll = C.ik_lower_leg;
+    const double lleg = lh - C.ik_hip_offset - C.ik_clip;
+    if (lleg > ul + ll) { out[0] = 0; out[1] = 0; return; }
+    double ca = (ul * ul + lleg * lleg - ll * ll) / (2 * ul * lleg);
+    ca = fmin(1.0, fmax(-1.0, ca));
+    const double hip = acos(ca);
+    double sa = ul * sin(hip) / ll;
+    sa = fmin(1.0, fmax(-1.0, sa));
+    out[0] = hip;
+    out[1] = -(asin(sa) + hip);
+}
+
+// per-env parameter draws for episode `ep` (randomizers/monopod.py:182-215); writes SoA params
+template <typename T>
+__device__ inline void draw_params(const TaskDev &K, StateDev<T> &S, int64_t e, uint64_t gid, uint32_t ep) {
+    const os2r_task_cfg &C = K.cfg;
+    const int64_t N = S.n_envs;
+    for (int i = 0; i < K.n_dof; ++i) {
+        double ms = 1.0, dm = K.nominal_damping[i], fr = K.nominal_friction[i];
+        if (C.randomize_params) {
+            ms = C.mass_lo + (C.mass_hi - C.mass_lo) * rng_uniform(S.seed, gid, ep, DRAW_PARAMS + i);
+            fr = C.fric_lo + (C.fric_hi - C.fric_lo) * rng_uniform(S.seed, gid, ep, DRAW_PARAMS + OS2R_MAX_DOF + i);
+            dm = K.nominal_damping[i] * (C.damp_lo + (C.damp_hi - C.damp_lo) * rng_uniform(S.seed, gid, ep, DRAW_PARAMS + 2 * OS2R_MAX_DOF + i));
+        }
+        S.mass_scale[i * N + e] = (T)ms;
+        S.damping[i * N + e] = (T)dm;
+        S.friction[i * N + e] = (T)fr;
+    }
+    for (int c = 0; c < K.n_contacts; ++c) {
+        double mu = K.nominal_mu[c];
+        if (C.randomize_params)
+            mu = C.mu_link * (C.mu_lo + (C.mu_hi - C.mu_lo) * rng_uniform(S.seed, gid, ep, DRAW_PARAMS + 3 * OS2R_MAX_DOF + c));
+        S.mu[c * N + e] = (T)mu;
+    }
+}
+
+// Reset pose draw (randomizers/monopod.py:67-135, monopod_no_rand.py:26-98). q[] in chain order.
+template <int N>
+__device__ inline int reset_pose(const TaskDev &K, uint64_t seed, uint64_t gid, uint32_t ep, double *q) {
+    const os2r_task_cfg &C = K.cfg;
+#pragma unroll
+    for (int i = 0; i < N; ++i) q[i] = 0;
+    int idx = (int)(rng_uniform(seed, gid, ep, DRAW_RESET) * C.n_resets);
+    if (idx >= C.n_resets) idx = C.n_resets - 1;
+    double pitch = C.reset_pitch[idx];
+    double leg[2];
+    double yaw = 0;
+    if (C.reset_randomized) {
+        pitch *= 0.8 + 0.4 * rng_uniform(seed, gid, ep, DRAW_PITCH);
+        double zz[2];
+        rng_normal2(seed, gid, ep, DRAW_NOISE, zz);
+        const double r0 = fabs(0.2 * zz[0]), r1 = fabs(0.2 * zz[1]);
+        const double rmax = r0 > r1 ? r0 : r1, rmin = r0 > r1 ? r1 : r0;
+        if (!C.reset_laying[idx]) leg_joint_angles(C, pitch, leg);
+        else { leg[0] = 1.57 - (rng_uniform(seed, gid, ep, DRAW_LAYSIDE) < 0.5 ? 3.14 : 0.0); leg[1] = 0; }
+        leg[0] = leg[0] + (leg[0] > 0 ? 1.0 : 0.0) * rmax;   // (a>0 - a<0) == (a>0): reference precedence quirk
+        leg[1] = leg[1] - (leg[1] > 0 ? 1.0 : 0.0) * rmin;
+        const double dir = 1.0 - (rng_uniform(seed, gid, ep, DRAW_DIR) < 0.5 ? 2.0 : 0.0);
+        leg[0] *= dir; leg[1] *= dir;
+        yaw = -0.2 + 0.4 * rng_uniform(seed, gid, ep, DRAW_YAW);
+    } else if (C.simple_sample_reset) {
+        leg[0] = C.simple_lo[0] + (C.simple_hi[0] - C.simple_lo[0]) * rng_uniform(seed, gid, ep, DRAW_SIMPLE_HIP);
+        leg[1] = C.simple_lo[1] + (C.simple_hi[1] - C.simple_lo[1]) * rng_uniform(seed, gid, ep, DRAW_SIMPLE_KNEE);
+    } else {
+        if (!C.reset_laying[idx]) leg_joint_angles(C, pitch, leg);
+        else { leg[0] = 1.57; leg[1] = 0; }
+    }
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        if (i == K.role_dof[OS2R_ROLE_YAW]) q[i] = yaw;
+        if (i == K.role_dof[OS2R_ROLE_PITCH]) q[i] = pitch;
+        if (i == K.role_dof[OS2R_ROLE_HIP]) q[i] = leg[0];
+        if (i == K.role_dof[OS2R_ROLE_KNEE]) q[i] = leg[1];
+    }
+    return idx;
+}
+
+}  // namespace os2r

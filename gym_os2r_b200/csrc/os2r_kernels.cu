@@ -1,0 +1,259 @@
+// os2r_kernels.cu — kernels of the monopod step path (sm_100a) and their launchers.
+#include "os2r_kernels.h"
+
+#include <math.h>
+
+namespace os2r {
+
+// ------------------------------------------------------------------------------------------------
+// reset of one env, written straight to the SoA state (rare path, fp64 draws shared with the oracle)
+// ------------------------------------------------------------------------------------------------
+template <typename T, int N, int NC>
+__device__ __noinline__ void reset_env_global(const TaskDev &K, StateDev<T> &S, int64_t e, const double *a_old,
+                                              float *obs_row) {
+    const int64_t NE = S.n_envs;
+    const uint64_t gid = (uint64_t)(S.first_env_id + e);
+    const uint32_t ep = S.episode[e] + 1u;
+    S.episode[e] = ep;
+    double q[N], v[N];
+    const int idx = reset_pose<N>(K, S.seed, gid, ep, q);
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        v[i] = 0.0;
+        const T hi = (T)q[i];
+        S.q_hi[i * NE + e] = hi;
+        S.q_lo[i * NE + e] = (sizeof(T) == 4) ? (T)(q[i] - (double)hi) : T(0);
+        S.qd[i * NE + e] = T(0);
+    }
+#pragma unroll
+    for (int r = 0; r < N + 3 * NC; ++r) S.lam[r * NE + e] = T(0);
+    S.reset_id[e] = idx;
+    S.steps[e] = 0;
+    S.ret[e] = 0.0;
+    draw_params<T>(K, S, e, gid, ep);
+    if (obs_row) {
+        // the observation sees the state the device will actually integrate (hi+lo rounding of q)
+        double qs[N];
+#pragma unroll
+        for (int i = 0; i < N; ++i) qs[i] = (double)S.q_hi[i * NE + e] + (double)S.q_lo[i * NE + e];
+        double o[OS2R_MAX_OBS];
+        observe<N>(K, qs, v, a_old, o);
+        for (int k = 0; k < K.cfg.obs_dim; ++k) obs_row[k] = (float)o[k];
+    }
+}
+
+template <typename T, int N, int NC>
+__global__ void __launch_bounds__(OS2R_BLOCK) reset_kernel(const __grid_constant__ TaskDev K, StateDev<T> S,
+                                                           const uint8_t *mask, float *obs) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= S.n_envs) return;
+    if (mask && !mask[e]) return;
+    const double a_old[2] = {(double)S.a_prev[e], (double)S.a_prev[S.n_envs + e]};
+    reset_env_global<T, N, NC>(K, S, e, a_old, obs ? obs + e * K.cfg.obs_dim : nullptr);
+}
+
+// nominal parameters + the once-per-env gravity draw (GazeboEnvRandomizer.__init__ -> randomize_physics)
+template <typename T>
+__global__ void __launch_bounds__(OS2R_BLOCK) init_kernel(const __grid_constant__ TaskDev K, StateDev<T> S, double nominal_gz) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t NE = S.n_envs;
+    if (e >= NE) return;
+    const uint64_t gid = (uint64_t)(S.first_env_id + e);
+    for (int i = 0; i < K.n_dof; ++i) {
+        S.q_hi[i * NE + e] = T(0); S.q_lo[i * NE + e] = T(0); S.qd[i * NE + e] = T(0);
+        S.mass_scale[i * NE + e] = T(1);
+        S.damping[i * NE + e] = (T)K.nominal_damping[i];
+        S.friction[i * NE + e] = (T)K.nominal_friction[i];
+    }
+    for (int c = 0; c < K.n_contacts; ++c) S.mu[c * NE + e] = (T)K.nominal_mu[c];
+    for (int r = 0; r < K.n_dof + 3 * K.n_contacts; ++r) S.lam[r * NE + e] = T(0);
+    S.a_prev[e] = T(0); S.a_prev[NE + e] = T(0);
+    double gz = nominal_gz;
+    if (K.cfg.randomize_gravity) {
+        double z[2];
+        rng_normal2(S.seed, gid, OS2R_EPISODE_GRAVITY, 0, z);
+        gz = K.cfg.grav_mean + K.cfg.grav_std * z[0];
+    }
+    S.gravity_z[e] = (T)gz;
+    S.steps[e] = 0; S.episode[e] = 0; S.reset_id[e] = 0; S.ret[e] = 0.0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// the fused step kernel: substeps x physics + observation + reward + done + auto-reset
+// ------------------------------------------------------------------------------------------------
+template <typename T, int N, int NC>
+__global__ void __launch_bounds__(OS2R_BLOCK, (sizeof(T) == 4 ? OS2R_MIN_BLOCKS : 1))
+step_kernel(const __grid_constant__ ModelDev<T> M, const __grid_constant__ TaskDev K, StateDev<T> S,
+            const float *__restrict__ actions, float *__restrict__ obs, float *__restrict__ reward,
+            uint8_t *__restrict__ done, float *__restrict__ term_obs, int32_t *__restrict__ info,
+            StatsDev *stats) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t NE = S.n_envs;
+    if (e >= NE) return;
+    constexpr int ROWS = N + 3 * NC;
+
+    EnvRegs<T, N, NC> E;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        E.q_hi[i] = S.q_hi[i * NE + e];
+        E.q_lo[i] = S.q_lo[i * NE + e];
+        E.v[i] = S.qd[i * NE + e];
+        E.mass_scale[i] = S.mass_scale[i * NE + e];
+        E.damping[i] = S.damping[i * NE + e];
+        E.fric_dt[i] = S.friction[i * NE + e] * M.dt;
+        E.tau[i] = T(0);
+    }
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) E.lam[r] = S.lam[r * NE + e];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) E.mu[c] = S.mu[c * NE + e];
+    E.gz = S.gravity_z[e];
+
+    float2 act = reinterpret_cast<const float2 *>(actions)[e];
+    // ScenarIO clips force targets to +-max force (tasks/monopod.py:313-316); a NaN action is left to
+    // the non-finite guard below.
+    act.x = fminf(1.0f, fmaxf(-1.0f, act.x));
+    act.y = fminf(1.0f, fmaxf(-1.0f, act.y));
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        if (i == M.hip_dof) E.tau[i] = M.max_torque[0] * (T)act.x;
+        if (i == M.knee_dof) E.tau[i] = M.max_torque[1] * (T)act.y;
+    }
+
+#pragma unroll 1
+    for (int s = 0; s < M.substeps; ++s) physics_iteration<T, N, NC>(M, E);
+
+    // ---- epilogue (fp64, once per env step) --------------------------------------------------------
+    double q[N], v[N];
+    bool finite = true;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        q[i] = (double)E.q_hi[i] + (double)E.q_lo[i];
+        v[i] = (double)E.v[i];
+        finite = finite && isfinite(q[i]) && isfinite(v[i]);
+    }
+    const double a0[2] = {(double)act.x, (double)act.y};
+    const double a_old[2] = {(double)S.a_prev[e], (double)S.a_prev[NE + e]};
+    double o[OS2R_MAX_OBS];
+    const bool task_done = observe<N>(K, q, v, a_old, o);
+    const double r = reward_fn(K.cfg, o, a0, a_old);
+    const int D = K.cfg.obs_dim;
+    int cause = task_done ? 1 : 0;
+    if (!finite) cause |= 4;
+    const int steps = S.steps[e] + 1;
+    const double ret = S.ret[e] + r;
+    if (K.cfg.max_episode_steps > 0 && steps >= K.cfg.max_episode_steps) cause |= 2;
+
+    reward[e] = (float)r;
+    done[e] = cause != 0;
+    if (term_obs) for (int k = 0; k < D; ++k) term_obs[e * D + k] = (float)o[k];
+    S.a_prev[e] = (T)act.x;
+    S.a_prev[NE + e] = (T)act.y;
+
+    if (cause) {
+        atomicAdd(&stats->episodes, 1ull);
+        if (cause & 1) atomicAdd(&stats->done_task, 1ull);
+        if (cause & 2) atomicAdd(&stats->done_timelimit, 1ull);
+        if (cause & 4) atomicAdd(&stats->nonfinite_resets, 1ull);
+        atomicAdd(&stats->sum_return, ret);
+        atomicAdd(&stats->sum_length, (double)steps);
+    }
+    if (cause && (K.cfg.auto_reset || !finite)) {
+        reset_env_global<T, N, NC>(K, S, e, a_old, obs + e * D);
+    } else {
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            S.q_hi[i * NE + e] = E.q_hi[i];
+            S.q_lo[i * NE + e] = E.q_lo[i];
+            S.qd[i * NE + e] = E.v[i];
+        }
+#pragma unroll
+        for (int rr = 0; rr < ROWS; ++rr) S.lam[rr * NE + e] = E.lam[rr];
+        S.steps[e] = steps;
+        S.ret[e] = ret;
+        for (int k = 0; k < D; ++k) obs[e * D + k] = (float)o[k];
+    }
+    if (info) {
+        info[2 * e] = S.reset_id[e];
+        info[2 * e + 1] = cause;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// fp32 FMA-pipe peak microbenchmark (roofline denominator; MEASURED_PEAKS.json has no fp32 entry)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) fma_peak_kernel(float *out, int iters, float seed) {
+    float a0 = seed + threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const float m = 0.999f, c = 1e-3f;
+#pragma unroll 1
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            a0 = fmaf(a0, m, c); a1 = fmaf(a1, m, c); a2 = fmaf(a2, m, c); a3 = fmaf(a3, m, c);
+            a4 = fmaf(a4, m, c); a5 = fmaf(a5, m, c); a6 = fmaf(a6, m, c); a7 = fmaf(a7, m, c);
+        }
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+// ------------------------------------------------------------------------------------------------
+// launchers (dispatch on n_dof; all shipped models carry 3 contact proxies)
+// ------------------------------------------------------------------------------------------------
+static inline int grid_for(int64_t n) { return (int)((n + OS2R_BLOCK - 1) / OS2R_BLOCK); }
+
+#define OS2R_DISPATCH_N(n_dof, CALL)                 \
+    switch (n_dof) {                                 \
+    case 2: { constexpr int N_ = 2; CALL; } break;   \
+    case 3: { constexpr int N_ = 3; CALL; } break;   \
+    case 4: { constexpr int N_ = 4; CALL; } break;   \
+    case 5: { constexpr int N_ = 5; CALL; } break;   \
+    default: return cudaErrorInvalidValue;           \
+    }
+
+template <typename T>
+cudaError_t launch_step(int n_dof, int n_contacts, const ModelDev<T> &M, const TaskDev &K, const StateDev<T> &S,
+                        const float *actions, float *obs, float *reward, uint8_t *done, float *term_obs,
+                        int32_t *info, StatsDev *stats, cudaStream_t stream) {
+    if (n_contacts != OS2R_NC) return cudaErrorInvalidValue;
+    OS2R_DISPATCH_N(n_dof, (step_kernel<T, N_, OS2R_NC><<<grid_for(S.n_envs), OS2R_BLOCK, 0, stream>>>(
+                               M, K, S, actions, obs, reward, done, term_obs, info, stats)));
+    return cudaGetLastError();
+}
+
+template <typename T>
+cudaError_t launch_reset(int n_dof, int n_contacts, const TaskDev &K, const StateDev<T> &S, const uint8_t *mask,
+                         float *obs, cudaStream_t stream) {
+    if (n_contacts != OS2R_NC) return cudaErrorInvalidValue;
+    OS2R_DISPATCH_N(n_dof, (reset_kernel<T, N_, OS2R_NC><<<grid_for(S.n_envs), OS2R_BLOCK, 0, stream>>>(K, S, mask, obs)));
+    return cudaGetLastError();
+}
+
+template <typename T>
+cudaError_t launch_init(const TaskDev &K, const StateDev<T> &S, double nominal_gz, cudaStream_t stream) {
+    init_kernel<T><<<grid_for(S.n_envs), OS2R_BLOCK, 0, stream>>>(K, S, nominal_gz);
+    return cudaGetLastError();
+}
+
+template <typename T>
+cudaError_t step_kernel_attributes(int n_dof, cudaFuncAttributes *attr) {
+    OS2R_DISPATCH_N(n_dof, return cudaFuncGetAttributes(attr, step_kernel<T, N_, OS2R_NC>));
+    return cudaSuccess;
+}
+
+cudaError_t launch_fma_peak(float *out, int blocks, int iters, cudaStream_t stream) {
+    fma_peak_kernel<<<blocks, 256, 0, stream>>>(out, iters, 1.0f);
+    return cudaGetLastError();
+}
+
+#define OS2R_INSTANTIATE(T)                                                                                   \
+    template cudaError_t launch_step<T>(int, int, const ModelDev<T> &, const TaskDev &, const StateDev<T> &,  \
+                                        const float *, float *, float *, uint8_t *, float *, int32_t *,       \
+                                        StatsDev *, cudaStream_t);                                            \
+    template cudaError_t launch_reset<T>(int, int, const TaskDev &, const StateDev<T> &, const uint8_t *,     \
+                                         float *, cudaStream_t);                                              \
+    template cudaError_t launch_init<T>(const TaskDev &, const StateDev<T> &, double, cudaStream_t);          \
+    template cudaError_t step_kernel_attributes<T>(int, cudaFuncAttributes *);
+OS2R_INSTANTIATE(float)
+OS2R_INSTANTIATE(double)
+
+}  // namespace os2r

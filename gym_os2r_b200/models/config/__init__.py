@@ -11,13 +11,23 @@ import os
 import yaml
 
 
+def _unshare(node):
+    """Recursive copy WITHOUT a memo: YAML aliases (one object referenced many times) become
+    independent containers (copy.deepcopy would preserve the sharing)."""
+    if isinstance(node, dict):
+        return {k: _unshare(v) for k, v in node.items()}
+    if isinstance(node, list):
+        return [_unshare(v) for v in node]
+    return node
+
+
 class BaseConfig:
     def __init__(self, yaml_path: str):
         here = os.path.dirname(os.path.abspath(__file__))
         with open(os.path.join(here, yaml_path)) as f:
             loaded = yaml.safe_load(f)
         # drop the anchor-holder keys ("_hip", ...) and un-share aliased containers
-        self.config_dict = copy.deepcopy({k: v for k, v in loaded.items() if not k.startswith('_')})
+        self.config_dict = _unshare({k: v for k, v in loaded.items() if not k.startswith('_')})
 
     @staticmethod
     def _split(xpath: str):

@@ -1,0 +1,3 @@
+from . import configure, cuda_runtime, engine, shims
+
+__all__ = ['cuda_runtime', 'engine', 'configure', 'shims']

@@ -9,13 +9,12 @@ from ..tasks.monopod import build_task_cfg
 def configure(task_cls, agent_rate: float = 1000, physics_rate: float = 10000, *,
               max_episode_steps: int = 0, auto_reset: bool = False, reset_randomized: bool = False,
               randomize_params: bool = False, randomize_gravity: bool = False, randomization: dict = None,
-              pgs_iters: int = None, **task_kwargs) -> Tuple[object, compiler.CompiledModel, _capi.TaskCfg]:
+              pgs_iters: int = None, substeps: int = None, **task_kwargs) -> Tuple[object, compiler.CompiledModel, _capi.TaskCfg]:
     """Create the task, its spaces, the compiled model tables and the device task configuration."""
     task = task_cls(agent_rate=agent_rate, **task_kwargs)
     task.create_spaces()
     physics = task.cfg.get_config('physics')
-    substeps = physics_rate / agent_rate
-    physics['substeps'] = int(substeps)          # gazebo_runtime.py:46-55 (rounds down, warns)
+    physics['substeps'] = int(physics_rate / agent_rate) if substeps is None else int(substeps)  # gazebo_runtime.py:46-55
     physics['dt'] = 1.0 / physics_rate
     if pgs_iters is not None:
         physics['pgs_iters'] = int(pgs_iters)

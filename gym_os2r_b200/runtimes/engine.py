@@ -1,0 +1,158 @@
+"""Thin object wrapper over the C-ABI handle (``os2r_env``): device buffers are torch tensors, the
+work is done by libos2r.so. This is plumbing, not a fallback: every method raises if the CUDA
+library or a CUDA device is missing."""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from .. import _capi
+
+
+class Engine:
+    """N monopod environments resident on one GPU.
+
+    ``step`` consumes / produces CUDA tensors on the current torch stream (asynchronous);
+    ``step_host`` consumes / produces numpy arrays (H2D + kernel + D2H inside, synchronous).
+    """
+
+    def __init__(self, compiled_model, task_cfg: _capi.TaskCfg, n_envs: int, device: int = 0, seed: int = 0,
+                 first_env_id: int = 0, precision: int = 32):
+        self.lib = _capi.load_library()
+        if not torch.cuda.is_available():
+            raise _capi.Os2rError('no CUDA device visible to torch; the monopod step path has no CPU fallback')
+        self.compiled = compiled_model
+        self.model = compiled_model.struct
+        self.task_cfg = task_cfg
+        self.n_envs = int(n_envs)
+        self.device_index = int(device)
+        self.device = torch.device('cuda', self.device_index)
+        self.obs_dim = int(task_cfg.obs_dim)
+        self.state_width = _capi.state_width(self.model)
+        self.params_width = _capi.params_width(self.model)
+        handle = C.c_void_p()
+        torch.cuda.init()
+        with torch.cuda.device(self.device):
+            torch.zeros(1, device=self.device)        # make sure the primary context exists
+            _capi.check(self.lib.os2r_create(C.byref(self.model), C.byref(task_cfg), self.n_envs, int(first_env_id),
+                                             self.device_index, int(seed) & (2 ** 64 - 1), int(precision),
+                                             C.byref(handle)), self.lib)
+        self.handle = handle
+        N, D = self.n_envs, self.obs_dim
+        kw = dict(device=self.device)
+        self.obs = torch.zeros((N, D), dtype=torch.float32, **kw)
+        self.reward = torch.zeros(N, dtype=torch.float32, **kw)
+        self.done_u8 = torch.zeros(N, dtype=torch.uint8, **kw)
+        self.terminal_obs = torch.zeros((N, D), dtype=torch.float32, **kw)
+        self.info = torch.zeros((N, 2), dtype=torch.int32, **kw)
+
+    # ------------------------------------------------------------------ lifecycle
+    def close(self):
+        if getattr(self, 'handle', None) is not None and self.handle:
+            self.lib.os2r_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def seed(self, seed: int):
+        _capi.check(self.lib.os2r_seed(self.handle, int(seed) & (2 ** 64 - 1)), self.lib)
+
+    # ------------------------------------------------------------------ hot path
+    def reset(self, mask: torch.Tensor = None) -> torch.Tensor:
+        m = None
+        if mask is not None:
+            m = mask.to(device=self.device, dtype=torch.uint8).contiguous()
+            assert m.shape == (self.n_envs,)
+        _capi.check(self.lib.os2r_reset(self.handle, C.c_void_p(m.data_ptr()) if m is not None else None,
+                                        C.c_void_p(self.obs.data_ptr()), self._stream()), self.lib)
+        return self.obs
+
+    def step(self, actions: torch.Tensor, want_terminal_obs: bool = True, want_info: bool = True):
+        """actions: float32 CUDA tensor [N, 2]. Returns views of the persistent output tensors."""
+        if actions.dtype != torch.float32 or not actions.is_cuda or not actions.is_contiguous():
+            actions = actions.to(device=self.device, dtype=torch.float32).contiguous()
+        if tuple(actions.shape) != (self.n_envs, 2):
+            raise ValueError(f'actions must have shape ({self.n_envs}, 2), got {tuple(actions.shape)}')
+        _capi.check(self.lib.os2r_step(
+            self.handle, C.c_void_p(actions.data_ptr()), C.c_void_p(self.obs.data_ptr()),
+            C.c_void_p(self.reward.data_ptr()), C.c_void_p(self.done_u8.data_ptr()),
+            C.c_void_p(self.terminal_obs.data_ptr()) if want_terminal_obs else None,
+            C.c_void_p(self.info.data_ptr()) if want_info else None, self._stream()), self.lib)
+        return self.obs, self.reward, self.done_u8, self.info
+
+    def step_host(self, actions: np.ndarray, want_terminal_obs: bool = False, want_info: bool = False):
+        """numpy in / numpy out (fresh arrays each call): H2D + kernel + D2H inside os2r_step_host."""
+        a = np.ascontiguousarray(actions, dtype=np.float32)
+        if a.shape != (self.n_envs, 2):
+            raise ValueError(f'actions must have shape ({self.n_envs}, 2), got {a.shape}')
+        N, D = self.n_envs, self.obs_dim
+        obs = np.empty((N, D), dtype=np.float32)
+        rew = np.empty(N, dtype=np.float32)
+        done = np.empty(N, dtype=np.bool_)
+        term = np.empty((N, D), dtype=np.float32) if want_terminal_obs else None
+        info = np.empty((N, 2), dtype=np.int32) if want_info else None
+        p = lambda x: x.ctypes.data_as(C.c_void_p) if x is not None else None
+        _capi.check(self.lib.os2r_step_host(self.handle, p(a), p(obs), p(rew), p(done), p(term), p(info)), self.lib)
+        return obs, rew, done, term, info
+
+    # ------------------------------------------------------------------ state access
+    def get_state(self) -> np.ndarray:
+        out = np.empty((self.n_envs, self.state_width), dtype=np.float64)
+        _capi.check(self.lib.os2r_get_state(self.handle, out.ctypes.data_as(C.c_void_p)), self.lib)
+        return out
+
+    def set_state(self, state: np.ndarray):
+        s = np.ascontiguousarray(state, dtype=np.float64)
+        assert s.shape == (self.n_envs, self.state_width), s.shape
+        _capi.check(self.lib.os2r_set_state(self.handle, s.ctypes.data_as(C.c_void_p)), self.lib)
+
+    def get_params(self) -> np.ndarray:
+        out = np.empty((self.n_envs, self.params_width), dtype=np.float64)
+        _capi.check(self.lib.os2r_get_params(self.handle, out.ctypes.data_as(C.c_void_p)), self.lib)
+        return out
+
+    def set_params(self, params: np.ndarray):
+        p = np.ascontiguousarray(params, dtype=np.float64)
+        assert p.shape == (self.n_envs, self.params_width), p.shape
+        _capi.check(self.lib.os2r_set_params(self.handle, p.ctypes.data_as(C.c_void_p)), self.lib)
+
+    def get_episode(self):
+        steps = np.empty(self.n_envs, dtype=np.int32)
+        ret = np.empty(self.n_envs, dtype=np.float64)
+        _capi.check(self.lib.os2r_get_episode(self.handle, steps.ctypes.data_as(C.c_void_p),
+                                              ret.ctypes.data_as(C.c_void_p), None), self.lib)
+        return steps, ret
+
+    def get_reset_ids(self) -> np.ndarray:
+        ids = np.empty(self.n_envs, dtype=np.int32)
+        _capi.check(self.lib.os2r_get_episode(self.handle, None, None, ids.ctypes.data_as(C.c_void_p)), self.lib)
+        return ids
+
+    def stats(self, clear: bool = False) -> dict:
+        s = _capi.Stats()
+        _capi.check(self.lib.os2r_stats_read(self.handle, C.byref(s), int(clear)), self.lib)
+        return {name: getattr(s, name) for name, _ in _capi.Stats._fields_}
+
+    def kernel_info(self) -> dict:
+        vals = [C.c_int32() for _ in range(4)]
+        _capi.check(self.lib.os2r_kernel_info(self.handle, *[C.byref(v) for v in vals]), self.lib)
+        return dict(zip(('block_threads', 'grid_blocks', 'regs_per_thread', 'local_bytes_per_thread'),
+                        (v.value for v in vals)))
+
+    @property
+    def kernel_launches(self) -> int:
+        return int(self.lib.os2r_kernel_launches(self.handle))
+
+
+def measure_fp32_peak(device: int = 0):
+    lib = _capi.load_library()
+    tf, mhz = C.c_double(), C.c_double()
+    _capi.check(lib.os2r_measure_fp32_peak(int(device), C.byref(tf), C.byref(mhz)), lib)
+    return tf.value, mhz.value

@@ -191,8 +191,9 @@ int32_t os2r_get_state(os2r_env *env, double *state_host);
 int32_t os2r_set_state(os2r_env *env, const double *state_host);
 int32_t os2r_get_params(os2r_env *env, double *params_host);
 int32_t os2r_set_params(os2r_env *env, const double *params_host);
-/* Per-env episode counters: steps[N] (int32), returns[N] (double). Either may be NULL. */
-int32_t os2r_get_episode(os2r_env *env, int32_t *steps_host, double *returns_host);
+/* Per-env episode bookkeeping: steps[N] (int32), returns[N] (double), reset_ids[N] (int32 index
+ * into the task's reset_positions = info['reset_orientation'], tasks/monopod.py:374). Any may be NULL. */
+int32_t os2r_get_episode(os2r_env *env, int32_t *steps_host, double *returns_host, int32_t *reset_ids_host);
 
 int32_t os2r_stats_read(os2r_env *env, os2r_stats *out, int32_t clear);
 

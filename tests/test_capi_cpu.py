@@ -1,0 +1,105 @@
+"""CPU suite: the C-ABI library loads and exports every symbol include/os2r.h declares, the ctypes
+mirrors have the C layout, and the product fails loudly (no CPU fallback) without a CUDA device."""
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+import pytest
+import torch
+
+from gym_os2r_b200 import _capi
+
+from helpers import make_config
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, 'include', 'os2r.h')
+
+
+@pytest.fixture(scope='module')
+def lib():
+    if not os.path.exists(_capi.LIB_PATH):
+        subprocess.check_call(['make', '-C', os.path.join(ROOT, 'gym_os2r_b200', 'csrc')])
+    return _capi.load_library()
+
+
+def test_every_declared_symbol_is_exported(lib):
+    text = open(HEADER).read()
+    text = re.sub(r'/\*.*?\*/', '', text, flags=re.S)
+    declared = set(re.findall(r'\b(os2r_[a-z0-9_]+)\s*\(', text))
+    assert len(declared) >= 20
+    assert declared == set(_capi.SYMBOLS), declared ^ set(_capi.SYMBOLS)
+    for name in declared:
+        assert getattr(lib, name) is not None
+    assert lib.os2r_abi_version() == _capi.ABI_VERSION
+
+
+def test_ctypes_layout_matches_header():
+    """Compile a tiny C program against include/os2r.h and compare sizeof / offsetof with ctypes."""
+    fields = {'os2r_model': (_capi.Model, ['n_dof', 'contact_body', 'tree_R', 'mass', 'inertia', 'contact_pos', 'gravity_z', 'max_torque']),
+              'os2r_task_cfg': (_capi.TaskCfg, ['obs_dim', 'obs_kind', 'reset_laying', 'obs_low', 'done_high', 'simple_lo', 'ik_clip', 'grav_std']),
+              'os2r_stats': (_capi.Stats, ['env_steps', 'sum_length'])}
+    prints = []
+    for sname, (_, fl) in fields.items():
+        prints.append(f'printf("%zu\\n", sizeof({sname}));')
+        prints += [f'printf("%zu\\n", offsetof({sname}, {f}));' for f in fl]
+    src = '#include <stdio.h>\n#include <stddef.h>\n#include "os2r.h"\nint main(void){' + ''.join(prints) + 'return 0;}'
+    with tempfile.TemporaryDirectory() as td:
+        cfile, exe = os.path.join(td, 't.c'), os.path.join(td, 't')
+        open(cfile, 'w').write(src)
+        subprocess.check_call(['gcc', '-I', os.path.join(ROOT, 'include'), cfile, '-o', exe])
+        nums = [int(x) for x in subprocess.check_output([exe]).split()]
+    it = iter(nums)
+    for sname, (cls, fl) in fields.items():
+        assert C.sizeof(cls) == next(it), sname
+        for f in fl:
+            assert getattr(cls, f).offset == next(it), (sname, f)
+
+
+def test_widths(lib):
+    task, cm, cfg = make_config('fixed_hip')
+    assert lib.os2r_state_width(C.byref(cm.struct)) == _capi.state_width(cm.struct) == 4 * 2 + 13 + 2
+    assert lib.os2r_params_width(C.byref(cm.struct)) == _capi.params_width(cm.struct) == 16
+
+
+def test_create_rejects_bad_arguments(lib):
+    task, cm, cfg = make_config('fixed_hip')
+    h = C.c_void_p()
+    assert lib.os2r_create(C.byref(cm.struct), C.byref(cfg), 0, 0, 0, 1, 32, C.byref(h)) != 0
+    assert b'n_envs' in lib.os2r_last_error()
+    assert lib.os2r_create(C.byref(cm.struct), C.byref(cfg), 8, 0, 0, 1, 16, C.byref(h)) != 0
+    assert b'precision' in lib.os2r_last_error()
+    assert lib.os2r_step(None, None, None, None, None, None, None, None) != 0
+    assert b'null handle' in lib.os2r_last_error()
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason='checks the no-GPU failure mode')
+def test_no_cpu_fallback(lib):
+    """Without a CUDA device the product path must fail loudly, never fall back to a CPU implementation."""
+    task, cm, cfg = make_config('fixed_hip')
+    h = C.c_void_p()
+    assert lib.os2r_create(C.byref(cm.struct), C.byref(cfg), 8, 0, 0, 1, 32, C.byref(h)) != 0
+    assert b'no CPU fallback' in lib.os2r_last_error()
+    from gym_os2r_b200.runtimes.engine import Engine
+    with pytest.raises(_capi.Os2rError):
+        Engine(cm, cfg, 8)
+    import gym_os2r_b200
+    env = gym_os2r_b200.make('Monopod-balance-v1')
+    with pytest.raises(_capi.Os2rError):
+        env.reset()
+
+
+def test_product_never_imports_oracle():
+    """The oracle is test infrastructure: nothing under gym_os2r_b200/ may reference it."""
+    pkg = os.path.join(ROOT, 'gym_os2r_b200')
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(('.py', '.cu', '.cuh', '.h')):
+                text = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r'^\s*(import|from)\s+oracle\b', text, flags=re.M), f
+                assert 'os2r_oracle' not in text, f
+    code = 'import sys; import gym_os2r_b200; assert "oracle" not in sys.modules'
+    subprocess.check_call([sys.executable, '-c', code], cwd=ROOT)
