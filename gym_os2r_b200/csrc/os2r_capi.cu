@@ -7,6 +7,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <vector>
@@ -152,7 +153,7 @@ void carve(os2r_env *h, StateDev<T> &S) {
     const int n = h->model.n_dof, nc = h->model.n_contacts;
     size_t off = 0;
     auto take = [&](int count) { T *p = base + off; off += (size_t)count * N; return p; };
-    S.q_hi = take(n); S.q_lo = take(n); S.qd = take(n);
+    S.q_hi = take(n); S.q_lo = take(n); S.qd = take(n); S.qd_lo = take(n);
     S.lam = take(h->rows); S.a_prev = take(2);
     S.mass_scale = take(n); S.damping = take(n); S.friction = take(n);
     S.mu = take(nc); S.gravity_z = take(1);
@@ -162,7 +163,7 @@ void carve(os2r_env *h, StateDev<T> &S) {
 
 size_t real_elems(const os2r_model &m, int64_t N) {
     const int n = m.n_dof, nc = m.n_contacts;
-    return (size_t)(3 * n + (n + 3 * nc) + 2 + 3 * n + nc + 1) * (size_t)N;
+    return (size_t)(4 * n + (n + 3 * nc) + 2 + 3 * n + nc + 1) * (size_t)N;
 }
 
 int ensure_host_io(os2r_env *h) {
@@ -206,12 +207,12 @@ template <typename T>
 int get_state_impl(os2r_env *h, StateDev<T> &S, double *out) {
     const int n = h->model.n_dof, W = os2r_state_width(&h->model);
     const int64_t N = h->n;
-    std::vector<double> hi, lo, qd, lam, ap;
-    if (get_real(h, S.q_hi, n, hi) || get_real(h, S.q_lo, n, lo) || get_real(h, S.qd, n, qd) ||
+    std::vector<double> hi, lo, qd, qdl, lam, ap;
+    if (get_real(h, S.q_hi, n, hi) || get_real(h, S.q_lo, n, lo) || get_real(h, S.qd, n, qd) || get_real(h, S.qd_lo, n, qdl) ||
         get_real(h, S.lam, h->rows, lam) || get_real(h, S.a_prev, 2, ap)) return 1;
     for (int64_t e = 0; e < N; ++e) {
         double *row = out + e * W;
-        for (int i = 0; i < n; ++i) { row[i] = hi[i * N + e] + lo[i * N + e]; row[n + i] = qd[i * N + e]; }
+        for (int i = 0; i < n; ++i) { row[i] = hi[i * N + e] + lo[i * N + e]; row[n + i] = qd[i * N + e] + qdl[i * N + e]; }
         for (int r = 0; r < h->rows; ++r) row[2 * n + r] = lam[r * N + e];
         row[2 * n + h->rows] = ap[e];
         row[2 * n + h->rows + 1] = ap[N + e];
@@ -222,20 +223,22 @@ template <typename T>
 int set_state_impl(os2r_env *h, StateDev<T> &S, const double *in) {
     const int n = h->model.n_dof, W = os2r_state_width(&h->model);
     const int64_t N = h->n;
-    std::vector<double> hi((size_t)n * N), lo((size_t)n * N), qd((size_t)n * N), lam((size_t)h->rows * N), ap((size_t)2 * N);
+    std::vector<double> hi((size_t)n * N), lo((size_t)n * N), qd((size_t)n * N), qdl((size_t)n * N), lam((size_t)h->rows * N), ap((size_t)2 * N);
     for (int64_t e = 0; e < N; ++e) {
         const double *row = in + e * W;
         for (int i = 0; i < n; ++i) {
             const T h1 = (T)row[i];
             hi[i * N + e] = (double)h1;
             lo[i * N + e] = sizeof(T) == 4 ? (double)(T)(row[i] - (double)h1) : 0.0;
-            qd[i * N + e] = row[n + i];
+            const T v1 = (T)row[n + i];
+            qd[i * N + e] = (double)v1;
+            qdl[i * N + e] = sizeof(T) == 4 ? (double)(T)(row[n + i] - (double)v1) : 0.0;
         }
         for (int r = 0; r < h->rows; ++r) lam[r * N + e] = row[2 * n + r];
         ap[e] = row[2 * n + h->rows];
         ap[N + e] = row[2 * n + h->rows + 1];
     }
-    return put_real(h, S.q_hi, n, hi) || put_real(h, S.q_lo, n, lo) || put_real(h, S.qd, n, qd) ||
+    return put_real(h, S.q_hi, n, hi) || put_real(h, S.q_lo, n, lo) || put_real(h, S.qd, n, qd) || put_real(h, S.qd_lo, n, qdl) ||
            put_real(h, S.lam, h->rows, lam) || put_real(h, S.a_prev, 2, ap);
 }
 template <typename T>

@@ -24,6 +24,7 @@ __device__ __noinline__ void reset_env_global(const TaskDev &K, StateDev<T> &S, 
         S.q_hi[i * NE + e] = hi;
         S.q_lo[i * NE + e] = (sizeof(T) == 4) ? (T)(q[i] - (double)hi) : T(0);
         S.qd[i * NE + e] = T(0);
+        S.qd_lo[i * NE + e] = T(0);
     }
 #pragma unroll
     for (int r = 0; r < N + 3 * NC; ++r) S.lam[r * NE + e] = T(0);
@@ -60,7 +61,7 @@ __global__ void __launch_bounds__(OS2R_BLOCK) init_kernel(const __grid_constant_
     if (e >= NE) return;
     const uint64_t gid = (uint64_t)(S.first_env_id + e);
     for (int i = 0; i < K.n_dof; ++i) {
-        S.q_hi[i * NE + e] = T(0); S.q_lo[i * NE + e] = T(0); S.qd[i * NE + e] = T(0);
+        S.q_hi[i * NE + e] = T(0); S.q_lo[i * NE + e] = T(0); S.qd[i * NE + e] = T(0); S.qd_lo[i * NE + e] = T(0);
         S.mass_scale[i * NE + e] = T(1);
         S.damping[i * NE + e] = (T)K.nominal_damping[i];
         S.friction[i * NE + e] = (T)K.nominal_friction[i];
@@ -90,25 +91,12 @@ step_kernel(const __grid_constant__ ModelDev<T> M, const __grid_constant__ TaskD
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t NE = S.n_envs;
     if (e >= NE) return;
-    constexpr int ROWS = N + 3 * NC;
+    using SL = ColdSlots<N, NC>;
+    constexpr int ROWS = SL::ROWS;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const Cold<T> C{reinterpret_cast<T *>(smem_raw) + threadIdx.x, (int)blockDim.x};
 
-    EnvRegs<T, N, NC> E;
-#pragma unroll
-    for (int i = 0; i < N; ++i) {
-        E.q_hi[i] = S.q_hi[i * NE + e];
-        E.q_lo[i] = S.q_lo[i * NE + e];
-        E.v[i] = S.qd[i * NE + e];
-        E.mass_scale[i] = S.mass_scale[i * NE + e];
-        E.damping[i] = S.damping[i * NE + e];
-        E.fric_dt[i] = S.friction[i * NE + e] * M.dt;
-        E.tau[i] = T(0);
-    }
-#pragma unroll
-    for (int r = 0; r < ROWS; ++r) E.lam[r] = S.lam[r * NE + e];
-#pragma unroll
-    for (int c = 0; c < NC; ++c) E.mu[c] = S.mu[c * NE + e];
-    E.gz = S.gravity_z[e];
-
+    EnvRegs<T, N> E;
     float2 act = reinterpret_cast<const float2 *>(actions)[e];
     // ScenarIO clips force targets to +-max force (tasks/monopod.py:313-316); a NaN action is left to
     // the non-finite guard below.
@@ -116,20 +104,34 @@ step_kernel(const __grid_constant__ ModelDev<T> M, const __grid_constant__ TaskD
     act.y = fminf(1.0f, fmaxf(-1.0f, act.y));
 #pragma unroll
     for (int i = 0; i < N; ++i) {
-        if (i == M.hip_dof) E.tau[i] = M.max_torque[0] * (T)act.x;
-        if (i == M.knee_dof) E.tau[i] = M.max_torque[1] * (T)act.y;
+        E.q_hi[i] = S.q_hi[i * NE + e];
+        E.v[i] = S.qd[i * NE + e];
+        C(SL::QLO + i) = S.q_lo[i * NE + e];
+        C(SL::VLO + i) = S.qd_lo[i * NE + e];
+        C(SL::MASS + i) = S.mass_scale[i * NE + e];
+        C(SL::DAMP + i) = S.damping[i * NE + e];
+        C(SL::FRIC + i) = S.friction[i * NE + e] * M.dt;
+        T tau = T(0);
+        if (i == M.hip_dof) tau = M.max_torque[0] * (T)act.x;
+        if (i == M.knee_dof) tau = M.max_torque[1] * (T)act.y;
+        C(SL::TAU + i) = tau;
     }
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) C(SL::LAM + r) = S.lam[r * NE + e];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) C(SL::MU + c) = S.mu[c * NE + e];
+    E.gz = S.gravity_z[e];
 
 #pragma unroll 1
-    for (int s = 0; s < M.substeps; ++s) physics_iteration<T, N, NC>(M, E);
+    for (int s = 0; s < M.substeps; ++s) physics_iteration<T, N, NC>(M, E, C);
 
     // ---- epilogue (fp64, once per env step) --------------------------------------------------------
     double q[N], v[N];
     bool finite = true;
 #pragma unroll
     for (int i = 0; i < N; ++i) {
-        q[i] = (double)E.q_hi[i] + (double)E.q_lo[i];
-        v[i] = (double)E.v[i];
+        q[i] = (double)E.q_hi[i] + (double)C(SL::QLO + i);
+        v[i] = (double)E.v[i] + (double)C(SL::VLO + i);
         finite = finite && isfinite(q[i]) && isfinite(v[i]);
     }
     const double a0[2] = {(double)act.x, (double)act.y};
@@ -164,11 +166,12 @@ step_kernel(const __grid_constant__ ModelDev<T> M, const __grid_constant__ TaskD
 #pragma unroll
         for (int i = 0; i < N; ++i) {
             S.q_hi[i * NE + e] = E.q_hi[i];
-            S.q_lo[i * NE + e] = E.q_lo[i];
+            S.q_lo[i * NE + e] = C(SL::QLO + i);
             S.qd[i * NE + e] = E.v[i];
+            S.qd_lo[i * NE + e] = C(SL::VLO + i);
         }
 #pragma unroll
-        for (int rr = 0; rr < ROWS; ++rr) S.lam[rr * NE + e] = E.lam[rr];
+        for (int rr = 0; rr < ROWS; ++rr) S.lam[rr * NE + e] = C(SL::LAM + rr);
         S.steps[e] = steps;
         S.ret[e] = ret;
         for (int k = 0; k < D; ++k) obs[e * D + k] = (float)o[k];
@@ -215,7 +218,8 @@ cudaError_t launch_step(int n_dof, int n_contacts, const ModelDev<T> &M, const T
                         const float *actions, float *obs, float *reward, uint8_t *done, float *term_obs,
                         int32_t *info, StatsDev *stats, cudaStream_t stream) {
     if (n_contacts != OS2R_NC) return cudaErrorInvalidValue;
-    OS2R_DISPATCH_N(n_dof, (step_kernel<T, N_, OS2R_NC><<<grid_for(S.n_envs), OS2R_BLOCK, 0, stream>>>(
+    OS2R_DISPATCH_N(n_dof, (step_kernel<T, N_, OS2R_NC><<<grid_for(S.n_envs), OS2R_BLOCK,
+                                                          ColdSlots<N_, OS2R_NC>::COUNT * OS2R_BLOCK * sizeof(T), stream>>>(
                                M, K, S, actions, obs, reward, done, term_obs, info, stats)));
     return cudaGetLastError();
 }
