@@ -97,6 +97,17 @@ __device__ __forceinline__ double fmin_t(double a, double b) { return fmin(a, b)
 __device__ __forceinline__ float fmax_t(float a, float b) { return fmaxf(a, b); }
 __device__ __forceinline__ double fmax_t(double a, double b) { return fmax(a, b); }
 
+// sin / cos of a compensated angle hi + lo: sin(hi+lo) = s + lo*c, cos(hi+lo) = c - lo*s.
+// Deliberately NOT inlined: sincosf's range-reduction slow path is ~150 instructions, and the physics loop
+// calls this once per joint; one shared copy keeps the loop body inside the instruction cache.
+template <typename T>
+__device__ __noinline__ void joint_sincos(T hi, T lo, T *s_out, T *c_out) {
+    T s, c;
+    sincos_t(hi, &s, &c);
+    *s_out = s + lo * c;
+    *c_out = c - lo * s;
+}
+
 #define OS2R_CROSS(o, a, b)                    \
     do {                                       \
         (o)[0] = (a)[1] * (b)[2] - (a)[2] * (b)[1]; \
@@ -174,11 +185,10 @@ struct ColdSlots {
     static constexpr int COUNT = CX + 3 * NC;
 };
 
-template <typename T>
-struct Cold {                    // accessor: slot k of this thread
-    T *base;                     // &smem[threadIdx.x]
-    int stride;                  // blockDim.x
-    __device__ __forceinline__ T &operator()(int k) const { return base[k * stride]; }
+template <typename T, int STRIDE>
+struct Cold {                    // accessor: slot k of this thread (STRIDE = threads per block, compile time so
+    T *base;                     // that every access is base + immediate offset; base = &smem[threadIdx.x])
+    __device__ __forceinline__ T &operator()(int k) const { return base[k * STRIDE]; }
 };
 
 template <typename T, int N>
@@ -187,8 +197,8 @@ struct EnvRegs {                 // hot per-thread state
     T gz;                        // gravity z (negative)
 };
 
-template <typename T, int N, int NC>
-__device__ __forceinline__ void physics_iteration(const ModelDev<T> &M, EnvRegs<T, N> &E, const Cold<T> &C) {
+template <typename T, int N, int NC, typename ColdT>
+__device__ __forceinline__ void physics_iteration(const ModelDev<T> &M, EnvRegs<T, N> &E, const ColdT &C) {
     using SL = ColdSlots<N, NC>;
     const T dt = M.dt;
 
@@ -238,13 +248,7 @@ __device__ __forceinline__ void physics_iteration(const ModelDev<T> &M, EnvRegs<
                         A[3 * r + c] = R[3 * r] * tR[c] + R[3 * r + 1] * tR[3 + c] + R[3 * r + 2] * tR[6 + c];
             }
             T s, c;
-            sincos_t(E.q_hi[i], &s, &c);
-            if (sizeof(T) == 4) {   // compensated position: sin(hi+lo) = s + lo*c, cos(hi+lo) = c - lo*s
-                const T lo = C(SL::QLO + i);
-                const T s2 = s + lo * c;
-                c = c - lo * s;
-                s = s2;
-            }
+            joint_sincos(E.q_hi[i], sizeof(T) == 4 ? C(SL::QLO + i) : T(0), &s, &c);
 #pragma unroll
             for (int r = 0; r < 3; ++r) {
                 const T a1 = A[3 * r + 1], a2 = A[3 * r + 2];

@@ -94,7 +94,7 @@ step_kernel(const __grid_constant__ ModelDev<T> M, const __grid_constant__ TaskD
     using SL = ColdSlots<N, NC>;
     constexpr int ROWS = SL::ROWS;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const Cold<T> C{reinterpret_cast<T *>(smem_raw) + threadIdx.x, (int)blockDim.x};
+    const Cold<T, OS2R_BLOCK> C{reinterpret_cast<T *>(smem_raw) + threadIdx.x};
 
     EnvRegs<T, N> E;
     float2 act = reinterpret_cast<const float2 *>(actions)[e];
@@ -123,7 +123,7 @@ step_kernel(const __grid_constant__ ModelDev<T> M, const __grid_constant__ TaskD
     E.gz = S.gravity_z[e];
 
 #pragma unroll 1
-    for (int s = 0; s < M.substeps; ++s) physics_iteration<T, N, NC>(M, E, C);
+    for (int s = 0; s < M.substeps; ++s) physics_iteration<T, N, NC, Cold<T, OS2R_BLOCK>>(M, E, C);
 
     // ---- epilogue (fp64, once per env step) --------------------------------------------------------
     double q[N], v[N];
