@@ -115,7 +115,7 @@ SYMBOLS = {
     'os2r_measure_fp32_peak': (_i32, [_i32, C.POINTER(_f64), C.POINTER(_f64)]),
 }
 
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'csrc', 'libos2r.so')
+LIB_PATH = os.environ.get('OS2R_LIB') or os.path.join(os.path.dirname(os.path.abspath(__file__)), 'csrc', 'libos2r.so')
 _lib = None
 
 

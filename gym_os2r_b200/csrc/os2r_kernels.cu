@@ -83,7 +83,11 @@ __global__ void __launch_bounds__(OS2R_BLOCK) init_kernel(const __grid_constant_
 // the fused step kernel: substeps x physics + observation + reward + done + auto-reset
 // ------------------------------------------------------------------------------------------------
 template <typename T, int N, int NC>
+#ifdef OS2R_MAXNREG
+__global__ void __maxnreg__(OS2R_MAXNREG)
+#else
 __global__ void __launch_bounds__(OS2R_BLOCK, (sizeof(T) == 4 ? OS2R_MIN_BLOCKS : 1))
+#endif
 step_kernel(const __grid_constant__ ModelDev<T> M, const __grid_constant__ TaskDev K, StateDev<T> S,
             const float *__restrict__ actions, float *__restrict__ obs, float *__restrict__ reward,
             uint8_t *__restrict__ done, float *__restrict__ term_obs, int32_t *__restrict__ info,

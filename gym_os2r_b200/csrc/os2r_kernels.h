@@ -5,8 +5,12 @@
 // Launch geometry of the step kernel. 64-thread blocks: 65 536 envs -> 1024 blocks over 148 SMs =
 // 6.92 blocks/SM, so with >= 7 resident blocks/SM the whole batch is ONE balanced wave
 // (7 x 64 = 448 threads/SM => at most 65536/448 = 146 -> 144 registers per thread).
+#ifndef OS2R_BLOCK
 #define OS2R_BLOCK 64
+#endif
+#ifndef OS2R_MIN_BLOCKS
 #define OS2R_MIN_BLOCKS 7
+#endif
 #define OS2R_NC 3
 
 namespace os2r {

@@ -1,0 +1,150 @@
+"""CPU suite: cross-checks that pin the physics half of the oracle WITHOUT DART:
+an independent Lagrangian mass matrix, finite-difference Jacobians, energy conservation, static
+equilibrium, and the fixed-sweep PGS against the same sweeps run to convergence."""
+import numpy as np
+import pytest
+
+import oracle
+from gym_os2r_b200.models import compiler
+
+from helpers import make_config
+
+
+def _mass_matrix_numpy(cm, params, q):
+    """M = sum_b m Jv^T Jv + Jw^T (R I R^T) Jw from numpy forward kinematics (independent of the C code)."""
+    m = cm.struct
+    n = m.n_dof
+    Rs, ps, _ = compiler.forward_kinematics(m, q)
+    axes = []
+    R, p = np.eye(3), np.zeros(3)
+    for i in range(n):
+        Rt = np.array(m.tree_R[i][:]).reshape(3, 3)
+        A = (Rs[i - 1] if i else np.eye(3)) @ Rt
+        axes.append(A[:, m.axis[i]])
+    M = np.zeros((n, n))
+    for b in range(n):
+        mass = m.mass[b] * params[b]
+        c = ps[b] + Rs[b] @ np.array(m.com[b][:])
+        t = m.inertia[b]
+        Ib = np.array([[t[0], t[3], t[4]], [t[3], t[1], t[5]], [t[4], t[5], t[2]]])
+        Iw = Rs[b] @ Ib @ Rs[b].T
+        Jv, Jw = np.zeros((3, n)), np.zeros((3, n))
+        for j in range(b + 1):
+            Jv[:, j] = np.cross(axes[j], c - ps[j])
+            Jw[:, j] = axes[j]
+        M += mass * Jv.T @ Jv + Jw.T @ Iw @ Jw
+    return M
+
+
+@pytest.mark.parametrize('mode', ['simple', 'fixed', 'fixed_hip', 'free_hip'])
+def test_minv_matches_independent_mass_matrix(mode):
+    task, cm, cfg = make_config(mode, reward='StraightV1' if mode == 'simple' else 'BalancingV1')
+    m = cm.struct
+    rng = np.random.RandomState(0)
+    p = oracle.nominal_params(m)
+    p[:m.n_dof] = rng.uniform(0.8, 1.2, m.n_dof)
+    for _ in range(5):
+        q = rng.uniform(-2, 2, m.n_dof)
+        _, Minv, _, _ = oracle.dynamics_debug(m, p, q, np.zeros(m.n_dof), [0, 0])
+        M = _mass_matrix_numpy(cm, p, q)
+        np.testing.assert_allclose(Minv @ M, np.eye(m.n_dof), atol=1e-9)
+        assert np.abs(Minv - Minv.T).max() < 1e-9 and np.linalg.eigvalsh(M).min() > 0
+
+
+def test_forward_dynamics_satisfies_equation_of_motion():
+    """M qdd + h = tau with h from the oracle's own zero-torque solve: linearity in tau (ABA is consistent)."""
+    task, cm, cfg = make_config('free_hip', reward='BalancingV1')
+    m = cm.struct
+    n = m.n_dof
+    rng = np.random.RandomState(1)
+    p = oracle.nominal_params(m)
+    q, v = rng.uniform(-1, 1, n), rng.uniform(-2, 2, n)
+    M = _mass_matrix_numpy(cm, p, q)
+    a0 = oracle.forward_dynamics_plain(m, p, q, v, np.zeros(n))
+    for _ in range(4):
+        tau = rng.uniform(-3, 3, n)
+        a = oracle.forward_dynamics_plain(m, p, q, v, tau)
+        np.testing.assert_allclose(M @ (a - a0), tau, atol=1e-9)
+
+
+def test_contact_jacobian_matches_finite_differences():
+    task, cm, cfg = make_config('fixed_hip', reward='BalancingV1')
+    m = cm.struct
+    n = m.n_dof
+    q = np.array([0.1, -0.03, 1.0, -2.2])       # lying: contacts penetrate so rows are built
+    _, _, depth, J = oracle.dynamics_debug(m, oracle.nominal_params(m), q, np.zeros(n), [0, 0])
+    assert (depth > 0).any()
+    eps = 1e-6
+    for c in range(m.n_contacts):
+        if depth[c] <= 0:
+            assert np.all(J[n + 3 * c:n + 3 * c + 3] == 0)
+            continue
+        Rs, ps, _ = compiler.forward_kinematics(m, q)
+        for i in range(n):
+            dq = np.zeros(n); dq[i] = eps
+            _, cp = oracle.fk(m, q + dq)
+            _, cm_ = oracle.fk(m, q - dq)
+            d = (cp[c] - cm_[c]) / (2 * eps)            # velocity of the sphere CENTRE per unit joint rate
+            # the constraint acts at the lowest point of the sphere (centre - r z): add axis x (-r z)
+            Rt = np.array(m.tree_R[i][:]).reshape(3, 3)
+            axis = ((Rs[i - 1] if i else np.eye(3)) @ Rt)[:, m.axis[i]]
+            if i <= m.contact_body[c]:
+                d = d + np.cross(axis, [0, 0, -m.contact_radius[c]])
+            np.testing.assert_allclose(J[n + 3 * c:n + 3 * c + 3, i], [d[2], d[0], d[1]], atol=1e-7)
+
+
+def test_energy_conservation_rk4():
+    """Undamped, frictionless, torque-free, contact-free motion integrated with RK4 at dt = 1e-4 conserves energy."""
+    task, cm, cfg = make_config('free_hip', reward='BalancingV1')
+    m = cm.struct
+    n = m.n_dof
+    p = oracle.nominal_params(m)
+    p[n:3 * n] = 0.0
+    rng = np.random.RandomState(0)
+    x = np.concatenate([rng.uniform(-1, 1, n), rng.uniform(-1, 1, n)])
+    x[1] = 0.6
+    f = lambda s: np.concatenate([s[n:], oracle.forward_dynamics_plain(m, p, s[:n], s[n:], np.zeros(n))])
+    e0 = oracle.energy(m, p, x[:n], x[n:])
+    h = 1e-4
+    for _ in range(600):
+        k1 = f(x); k2 = f(x + h / 2 * k1); k3 = f(x + h / 2 * k2); k4 = f(x + h * k3)
+        x = x + h / 6 * (k1 + 2 * k2 + 2 * k3 + k4)
+    assert abs(oracle.energy(m, p, x[:n], x[n:]) - e0) < 1e-11 * max(1.0, abs(e0))
+
+
+def test_static_stand_normal_force():
+    """Monopod resting on its foot with locked-ish leg: total normal impulse per iteration = supported weight * dt
+    (moment balance about the pitch axis gives ~7 N at the foot; SURVEY.md section 8c cross-check iv)."""
+    task, cm, cfg = make_config('fixed_hip', reward='BalancingV1')
+    m = cm.struct
+    n = m.n_dof
+    p = oracle.nominal_params(m)
+    p[2 * n:3 * n] = 5.0     # strong joint friction holds the leg pose so the system settles on the foot
+    q = np.zeros(n)
+    q[cm.dof_of('planarizer_pitch_joint')], q[cm.dof_of('hip_joint')], q[cm.dof_of('knee_joint')] = 0.12, 0.6375366, -1.3146489
+    v, lam = np.zeros(n), np.zeros(n + 9)
+    q, v, lam = oracle.substeps(m, p, q, v, lam, [0, 0], 4000)
+    foot_force = lam[n + 6] / m.dt
+    assert 5.0 < foot_force < 9.0, foot_force
+    assert np.abs(v).max() < 1e-2
+
+
+def test_fixed_sweeps_track_converged_lcp():
+    """8 warm-started sweeps per iteration stay close to the same PGS run to convergence."""
+    task, cm, cfg = make_config('fixed_hip', reward='BalancingV1')
+    m = cm.struct
+    n = m.n_dof
+    p = oracle.nominal_params(m)
+    q0 = np.zeros(n)
+    q0[cm.dof_of('planarizer_pitch_joint')], q0[cm.dof_of('hip_joint')], q0[cm.dof_of('knee_joint')] = 0.15, 0.2861, -0.5877
+    rng = np.random.RandomState(5)
+    acts = 0.1 * rng.uniform(-1, 1, (120, 2))
+
+    def roll(sweeps, tol):
+        q, v, lam = q0.copy(), np.zeros(n), np.zeros(n + 9)
+        for a in acts:
+            q, v, lam = oracle.substeps(m, p, q, v, lam, a, 10, sweeps=sweeps, tol=tol)
+        return q
+    ref = roll(4000, 1e-16)
+    assert np.abs(roll(8, 0.0) - ref).max() < 2e-3      # ~30 steps after touchdown
+    assert np.abs(roll(8, 0.0) - ref).max() < np.abs(roll(2, 0.0) - ref).max()
