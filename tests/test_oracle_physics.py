@@ -119,13 +119,14 @@ def test_static_stand_normal_force():
     m = cm.struct
     n = m.n_dof
     p = oracle.nominal_params(m)
-    p[2 * n:3 * n] = 5.0     # strong joint friction holds the leg pose so the system settles on the foot
+    p[2 * n:3 * n] = 0.0     # strong friction on hip and knee only: the leg holds its pose, the boom is free
+    p[2 * n + cm.dof_of('hip_joint')] = p[2 * n + cm.dof_of('knee_joint')] = 5.0
     q = np.zeros(n)
     q[cm.dof_of('planarizer_pitch_joint')], q[cm.dof_of('hip_joint')], q[cm.dof_of('knee_joint')] = 0.12, 0.6375366, -1.3146489
     v, lam = np.zeros(n), np.zeros(n + 9)
     q, v, lam = oracle.substeps(m, p, q, v, lam, [0, 0], 4000)
     foot_force = lam[n + 6] / m.dt
-    assert 5.0 < foot_force < 9.0, foot_force
+    assert 6.5 < foot_force < 7.7, foot_force
     assert np.abs(v).max() < 1e-2
 
 
