@@ -1,0 +1,165 @@
+"""GPU tests (-m gpu) of the reference-facing API: pytest translations of the reference's script-style
+tests/tests_general.py:12-160 (check_registered_envs, test_random_rollout, single_process,
+single_process_fixed_hip, test_monopod_model) plus the vector entry point and the torch policy loop."""
+import functools
+
+import numpy as np
+import pytest
+import torch
+
+import gym_os2r                                   # the drop-in alias package
+from gym_os2r import randomizers
+from gym_os2r.common import make_env_from_id, make_mp_envs
+from gym_os2r.rewards import RewardBase
+
+pytestmark = pytest.mark.gpu
+ENV_IDS = [s.id for s in gym_os2r._impl._gymshim.registry.all() if 'Monopod' in s.id]
+
+
+@pytest.mark.parametrize('env_id', ENV_IDS)
+def test_registered_env_contract(env_id):
+    """tests_general.py:12-58 — spaces, dtypes, scalar reward, bool done, render before/after close."""
+    env = randomizers.monopod.MonopodEnvRandomizer(env=functools.partial(make_env_from_id, env_id=env_id))
+    env.seed(42)
+    ob = env.reset()
+    assert env.observation_space.contains(ob), ob
+    assert ob.dtype == env.observation_space.dtype == np.float64
+    a = env.action_space.sample()
+    observation, reward, done, info = env.step(a)
+    assert env.observation_space.contains(observation)
+    assert np.isscalar(reward) and isinstance(done, bool) and observation.dtype == np.float64
+    assert info['reset_orientation'] in env.unwrapped.task.reset_positions
+    for mode in env.metadata.get('render.modes', []):
+        env.render(mode=mode)
+    env.close()
+    for mode in env.metadata.get('render.modes', []):
+        env.render(mode=mode)
+
+
+@pytest.mark.parametrize('env_id', ENV_IDS)
+def test_random_rollout(env_id):
+    """tests_general.py:61-78"""
+    env = randomizers.monopod.MonopodEnvRandomizer(env=functools.partial(make_env_from_id, env_id=env_id))
+    env.seed(42)
+    ob = env.reset()
+    for _ in range(10):
+        assert env.observation_space.contains(ob)
+        a = env.action_space.sample()
+        assert env.action_space.contains(a)
+        ob, _reward, done, _info = env.step(a)
+        if done:
+            break
+    env.close()
+
+
+@pytest.mark.parametrize('task_mode,dim', [('free_hip', 10), ('fixed_hip', 8)])
+def test_single_process(task_mode, dim):
+    """tests_general.py:81-125"""
+    make_env = functools.partial(make_env_from_id, env_id='Monopod-balance-v1', task_mode=task_mode)
+    env = randomizers.monopod_no_rand.MonopodEnvNoRandomizer(env=make_env)
+    env.seed(42)
+    observation = env.reset()
+    assert len(observation) == dim
+    assert env.get_state_info(observation, [0, 0])[1] is False
+    action = env.action_space.sample()
+    after, reward, done, _ = env.step(action)
+    assert env.get_state_info(after, action)[0] == reward
+    moving = [i for n, i in env.unwrapped.task.observation_index.items() if 'yaw' not in n and 'boom_connector' not in n]
+    assert all(after[moving] != observation[moving])
+    # Task methods are views of the fused launch (reference: recomputed three times per step)
+    task = env.unwrapped.task
+    assert np.array_equal(task.get_observation(), after) and task.get_reward() == reward and task.is_done() == done
+    env.close()
+
+
+def test_monopod_model_reset_determinism():
+    """tests_general.py:128-160"""
+    def resets(randomizer, poses, k):
+        env = randomizer(env=functools.partial(make_env_from_id, env_id='Monopod-balance-v1', reset_positions=poses))
+        env.seed(42)
+        out = np.vstack([env.reset() for _ in range(k)])
+        env.close()
+        return out
+    assert not (np.diff(resets(randomizers.monopod_no_rand.MonopodEnvNoRandomizer, ['stand', 'ground'], 9), axis=0) == 0).all()
+    assert (np.diff(resets(randomizers.monopod_no_rand.MonopodEnvNoRandomizer, ['stand'], 7), axis=0) == 0).all()
+    assert not (np.diff(resets(randomizers.monopod.MonopodEnvRandomizer, ['stand'], 2), axis=0) == 0).all()
+
+
+def test_custom_reward_class_runs_on_device():
+    """examples/minimal_example.py:15-29 — a user RewardBase subclass (torch-evaluated on the GPU)."""
+    class HeightV0(RewardBase):
+        def __init__(self, observation_index, normalized):
+            super().__init__(observation_index, normalized)
+            self.supported_task_modes = ['fixed_hip']
+
+        def calculate_reward(self, obs, actions):
+            return obs[..., self.observation_index['planarizer_pitch_joint_pos']] * 2 + 1
+    env = randomizers.monopod_no_rand.MonopodEnvNoRandomizer(env=functools.partial(
+        make_env_from_id, env_id='Monopod-balance-v1', task_mode='fixed_hip', reward_class=HeightV0))
+    env.reset()
+    ob, reward, done, _ = env.step([0.1, -0.1])
+    assert reward == pytest.approx(ob[2] * 2 + 1, abs=1e-6)
+    env.close()
+
+
+def test_vec_env_numpy_and_torch_paths_agree():
+    """make_mp_envs (common/__init__.py:27-53): numpy in/out, auto-reset with terminal_observation, seeds by rank."""
+    N = 512
+    kw = dict(task_mode='fixed_hip', max_episode_steps=6)
+    e_np = make_mp_envs('Monopod-balance-v1', N, 3, randomizers.monopod.MonopodEnvRandomizer, **kw)
+    e_t = make_mp_envs('Monopod-balance-v1', N, 3, randomizers.monopod.MonopodEnvRandomizer, **kw)
+    e_t.output = 'torch'
+    o1 = e_np.reset()
+    o2 = e_t.reset()
+    assert isinstance(o1, np.ndarray) and o1.shape == (N, 8) and np.array_equal(o1, o2.cpu().numpy())
+    assert e_np.observation_space.shape == (8,) and e_np.num_envs == N
+    rng = np.random.RandomState(0)
+    for t in range(7):
+        a = rng.uniform(-1, 1, (N, 2)).astype(np.float32)
+        obs, rew, done, infos = e_np.step(a)
+        obs_t, rew_t, done_t, info_t = e_t.step(torch.as_tensor(a, device='cuda'))
+        assert np.array_equal(obs, obs_t.cpu().numpy()) and np.array_equal(rew, rew_t.cpu().numpy())
+        assert np.array_equal(done, done_t.cpu().numpy())
+    assert done.dtype == np.bool_ and rew.shape == (N,)
+    e_np.step_async(a); obs, rew, done, infos = e_np.step_wait()
+    e_t.step(torch.as_tensor(a, device='cuda'))
+    # step 6 hit the TimeLimit for every env: terminal observation differs from the returned reset observation
+    e2 = make_mp_envs('Monopod-balance-v1', 4, 3, randomizers.monopod.MonopodEnvRandomizer, **kw)
+    e2.reset()
+    for t in range(6):
+        obs, rew, done, infos = e2.step(np.zeros((4, 2), np.float32))
+    assert done.all() and len(infos) == 4
+    assert infos[0]['TimeLimit.truncated'] and infos[0]['terminal_observation'].shape == (8,)
+    assert not np.array_equal(infos[0]['terminal_observation'], obs[0]) and infos[0]['reset_orientation'] == 'stand'
+    r, d = e2.get_state_info(obs, np.zeros((4, 2)))
+    assert r.shape == (4,) and d.shape == (4,) and not d.any()
+    for e in (e_np, e_t, e2):
+        e.close()
+
+
+def test_policy_rollout_stays_on_device_and_checkpoints():
+    """BASELINE config 5 shape (small): torch MLP -> step -> obs, all CUDA tensors; get_state/set_state resume."""
+    N = 4096
+    envs = make_mp_envs('Monopod-hop-v1', N, 1, randomizers.monopod.MonopodEnvRandomizer)
+    envs.output = 'torch'
+    obs = envs.reset()
+    policy = torch.nn.Sequential(torch.nn.Linear(10, 32), torch.nn.Tanh(), torch.nn.Linear(32, 2), torch.nn.Tanh()).cuda()
+    with torch.no_grad():
+        for _ in range(20):
+            obs, rew, done, info = envs.step(policy(obs))
+    assert obs.is_cuda and obs.shape == (N, 10) and rew.is_cuda and done.dtype == torch.bool
+    assert torch.isfinite(obs).all() and obs.abs().max() <= 1.0
+    rt = envs.runtime
+    snap = rt.get_state()
+    with torch.no_grad():
+        a = policy(obs)
+        o1 = envs.step(a)[0].clone()
+        rt.set_state(snap)
+        o2 = envs.step(a)[0].clone()
+    done_mask = envs.runtime.engine.done_u8.bool()
+    assert torch.equal(o1[~done_mask], o2[~done_mask])
+    # ScenarIO-style pokes (examples/ignition_interaction.py)
+    model = rt.task.model
+    assert len(model.joint_positions(['hip_joint', 'knee_joint'])) == 2
+    assert rt.world.to_gazebo().set_gravity((0, 0, -5.0)) and rt.world.gravity()[2] == -5.0
+    envs.close()
