@@ -182,12 +182,14 @@ def main():
     eng = rt.engine
     gen = torch.Generator(device=dev)
     gen.manual_seed(1234 + rank)
-    acts = [torch.rand((N, 2), device=dev, generator=gen) * 2 - 1 for _ in range(16)]
+    # fresh uniform actions every step (as action_space.sample() in examples/multiprocessing_epochs.py:22-23);
+    # a short cyclic pool would give every env a periodic torque with non-zero mean and spin the hip up.
+    new_actions = lambda: torch.rand((N, 2), device=dev, generator=gen) * 2 - 1
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
 
     fp32_peak, _ = measure_fp32_peak(local_rank)
     for i in range(max(W, 3)):
-        eng.step(acts[i % 16])
+        eng.step(new_actions())
     torch.cuda.synchronize(dev)
 
     sampler = ClockSampler(local_rank)
@@ -202,8 +204,9 @@ def main():
     wall0 = time.perf_counter()
     for i in range(K):
         flush.zero_()                      # L2 flush between timed iterations, outside the event pair
+        a = new_actions()                  # action generation (torch) is outside the event pair too
         ev0[i].record()
-        eng.step(acts[i % 16], want_terminal_obs=True, want_info=True)
+        eng.step(a, want_terminal_obs=True, want_info=True)
         ev1[i].record()
     torch.cuda.synchronize(dev)
     wall = time.perf_counter() - wall0
@@ -215,9 +218,10 @@ def main():
     total_ms = float(sum(per_step_ms))
     # hot-L2 variant: K back-to-back steps, no flush (state stays resident in the 126 MB L2)
     s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    pool = [new_actions() for _ in range(min(K, 512))]
     s0.record()
     for i in range(K):
-        eng.step(acts[i % 16])
+        eng.step(pool[i % len(pool)])
     s1.record()
     torch.cuda.synchronize(dev)
     hot_ms = s0.elapsed_time(s1)

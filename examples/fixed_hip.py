@@ -1,4 +1,9 @@
 """Single monopod, fixed hip, random actions — the reference's examples/fixed_hip.py on the CUDA runtime."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))  # run from a checkout
+
 import functools
 import time
 

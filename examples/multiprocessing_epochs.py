@@ -1,5 +1,10 @@
 """The reference's examples/multiprocessing_epochs.py: there NUM_ENVS = cpu_count() Gazebo processes, here
 65 536 monopods stepped by one fused kernel per step behind the same VecEnv calls."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))  # run from a checkout
+
 import time
 
 import numpy as np
@@ -13,7 +18,7 @@ envs.reset()
 returns = np.zeros(NUM_ENVS)
 episodes, steps, beg = 0, 0, time.time()
 rng = np.random.RandomState(0)
-while episodes < 1000:
+while episodes < 1000 and steps < 2000:
     actions = rng.uniform(-1, 1, (NUM_ENVS, 2)).astype(np.float32)
     obs, rew, done, infos = envs.step(actions)
     returns += rew

@@ -1,6 +1,11 @@
 """BASELINE config 5: device-resident rollout — a torch MLP policy feeds the fused step kernel, obs / reward /
 done never leave the GPU. One process per GPU under torchrun; episode statistics are all-reduced over NCCL."""
 import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))  # run from a checkout
+
+import os
 import time
 
 import torch
@@ -21,12 +26,19 @@ envs.output = 'torch'
 obs = envs.reset()
 policy = torch.nn.Sequential(torch.nn.Linear(obs.shape[1], 64), torch.nn.Tanh(), torch.nn.Linear(64, 64), torch.nn.Tanh(),
                              torch.nn.Linear(64, 2), torch.nn.Tanh()).cuda()
-steps = 200
-torch.cuda.synchronize(); t0 = time.time()
+steps, warmup = 500, 20
+static_obs = obs.clone()
 with torch.no_grad():
+    for _ in range(warmup):                       # cuBLAS / allocator warm-up before capture
+        static_obs.copy_(envs.step(policy(static_obs))[0])
+    # one CUDA graph = policy forward + fused env step (+ obs copy-back): the launch-bound inner loop
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        static_obs.copy_(envs.step(policy(static_obs))[0])
+    torch.cuda.synchronize(); t0 = time.time()
     for _ in range(steps):
-        obs, rew, done, info = envs.step(policy(obs))
-torch.cuda.synchronize(); dt = time.time() - t0
+        graph.replay()
+    torch.cuda.synchronize(); dt = time.time() - t0
 stats = reduce_stats(envs.runtime.engine.stats(), device=torch.device('cuda', local))
 if rank == 0:
     print(f'{world} GPU(s): {world * N * steps / dt / 1e6:.1f} M env-steps/s incl. policy; episodes={stats["episodes"]:.0f} '

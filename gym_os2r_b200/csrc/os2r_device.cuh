@@ -108,6 +108,14 @@ __device__ __noinline__ void joint_sincos(T hi, T lo, T *s_out, T *c_out) {
     *c_out = c - lo * s;
 }
 
+// bit-preserving int <-> T for parking integers in the T-typed shared-memory slots
+template <typename T> __device__ __forceinline__ T __int_as_float_t(int v);
+template <> __device__ __forceinline__ float __int_as_float_t<float>(int v) { return __int_as_float(v); }
+template <> __device__ __forceinline__ double __int_as_float_t<double>(int v) { return __hiloint2double(0, v); }
+template <typename T> __device__ __forceinline__ int __float_as_int_t(T v);
+template <> __device__ __forceinline__ int __float_as_int_t<float>(float v) { return __float_as_int(v); }
+template <> __device__ __forceinline__ int __float_as_int_t<double>(double v) { return __double2loint(v); }
+
 #define OS2R_CROSS(o, a, b)                    \
     do {                                       \
         (o)[0] = (a)[1] * (b)[2] - (a)[2] * (b)[1]; \
@@ -182,7 +190,9 @@ struct ColdSlots {
     static constexpr int QLO = TAU + N;           // [N]
     static constexpr int VLO = QLO + N;           // [N]
     static constexpr int CX = VLO + N;            // [3*NC] contact centres (world)
-    static constexpr int COUNT = CX + 3 * NC;
+    static constexpr int AOLD = CX + 3 * NC;      // [2] previous action (loaded in the prologue, used by the epilogue)
+    static constexpr int MISC = AOLD + 2;         // [3] episode step counter, episode return (lo, hi words)
+    static constexpr int COUNT = MISC + 3;
 };
 
 template <typename T, int STRIDE>

@@ -9,8 +9,8 @@ namespace os2r {
 // reset of one env, written straight to the SoA state (rare path, fp64 draws shared with the oracle)
 // ------------------------------------------------------------------------------------------------
 template <typename T, int N, int NC>
-__device__ __noinline__ void reset_env_global(const TaskDev &K, StateDev<T> &S, int64_t e, const double *a_old,
-                                              float *obs_row) {
+__device__ __noinline__ int reset_env_global(const TaskDev &K, StateDev<T> &S, int64_t e, const double *a_old,
+                                             float *obs_row) {
     const int64_t NE = S.n_envs;
     const uint64_t gid = (uint64_t)(S.first_env_id + e);
     const uint32_t ep = S.episode[e] + 1u;
@@ -41,6 +41,7 @@ __device__ __noinline__ void reset_env_global(const TaskDev &K, StateDev<T> &S, 
         observe<N>(K, qs, v, a_old, o);
         for (int k = 0; k < K.cfg.obs_dim; ++k) obs_row[k] = (float)o[k];
     }
+    return idx;
 }
 
 template <typename T, int N, int NC>
@@ -101,30 +102,55 @@ step_kernel(const __grid_constant__ ModelDev<T> M, const __grid_constant__ TaskD
     const Cold<T, OS2R_BLOCK> C{reinterpret_cast<T *>(smem_raw) + threadIdx.x};
 
     EnvRegs<T, N> E;
-    float2 act = reinterpret_cast<const float2 *>(actions)[e];
+    // ---- prologue: ALL global loads are issued back to back (explicit ld.global, so the compiler may hoist
+    //      them above the shared-memory stores that follow; generic loads were serialised LD -> STS -> LD ...,
+    //      one DRAM round trip each) and only then scattered into registers / shared memory.
+    T ld_qlo[N], ld_vlo[N], ld_mass[N], ld_damp[N], ld_fric[N], ld_lam[ROWS], ld_mu[NC];
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        E.q_hi[i] = __ldcg(S.q_hi + i * NE + e);
+        E.v[i] = __ldcg(S.qd + i * NE + e);
+        ld_qlo[i] = __ldcg(S.q_lo + i * NE + e);
+        ld_vlo[i] = __ldcg(S.qd_lo + i * NE + e);
+        ld_mass[i] = __ldcg(S.mass_scale + i * NE + e);
+        ld_damp[i] = __ldcg(S.damping + i * NE + e);
+        ld_fric[i] = __ldcg(S.friction + i * NE + e);
+    }
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) ld_lam[r] = __ldcg(S.lam + r * NE + e);
+#pragma unroll
+    for (int c = 0; c < NC; ++c) ld_mu[c] = __ldcg(S.mu + c * NE + e);
+    E.gz = __ldcg(S.gravity_z + e);
+    const T a_old0 = __ldcg(S.a_prev + e), a_old1 = __ldcg(S.a_prev + NE + e);
+    const int steps_in = __ldcg(S.steps + e);
+    int reset_idx = __ldcg(S.reset_id + e);
+    const double ret_in = __ldcg(S.ret + e);
+    float2 act = __ldcg(reinterpret_cast<const float2 *>(actions) + e);
     // ScenarIO clips force targets to +-max force (tasks/monopod.py:313-316); a NaN action is left to
     // the non-finite guard below.
     act.x = fminf(1.0f, fmaxf(-1.0f, act.x));
     act.y = fminf(1.0f, fmaxf(-1.0f, act.y));
 #pragma unroll
     for (int i = 0; i < N; ++i) {
-        E.q_hi[i] = S.q_hi[i * NE + e];
-        E.v[i] = S.qd[i * NE + e];
-        C(SL::QLO + i) = S.q_lo[i * NE + e];
-        C(SL::VLO + i) = S.qd_lo[i * NE + e];
-        C(SL::MASS + i) = S.mass_scale[i * NE + e];
-        C(SL::DAMP + i) = S.damping[i * NE + e];
-        C(SL::FRIC + i) = S.friction[i * NE + e] * M.dt;
+        C(SL::QLO + i) = ld_qlo[i];
+        C(SL::VLO + i) = ld_vlo[i];
+        C(SL::MASS + i) = ld_mass[i];
+        C(SL::DAMP + i) = ld_damp[i];
+        C(SL::FRIC + i) = ld_fric[i] * M.dt;
         T tau = T(0);
         if (i == M.hip_dof) tau = M.max_torque[0] * (T)act.x;
         if (i == M.knee_dof) tau = M.max_torque[1] * (T)act.y;
         C(SL::TAU + i) = tau;
     }
 #pragma unroll
-    for (int r = 0; r < ROWS; ++r) C(SL::LAM + r) = S.lam[r * NE + e];
+    for (int r = 0; r < ROWS; ++r) C(SL::LAM + r) = ld_lam[r];
 #pragma unroll
-    for (int c = 0; c < NC; ++c) C(SL::MU + c) = S.mu[c * NE + e];
-    E.gz = S.gravity_z[e];
+    for (int c = 0; c < NC; ++c) C(SL::MU + c) = ld_mu[c];
+    C(SL::AOLD) = a_old0;
+    C(SL::AOLD + 1) = a_old1;
+    C(SL::MISC) = __int_as_float_t<T>(steps_in);
+    C(SL::MISC + 1) = __int_as_float_t<T>(__double2loint(ret_in));
+    C(SL::MISC + 2) = __int_as_float_t<T>(__double2hiint(ret_in));
 
 #pragma unroll 1
     for (int s = 0; s < M.substeps; ++s) physics_iteration<T, N, NC, Cold<T, OS2R_BLOCK>>(M, E, C);
@@ -139,15 +165,15 @@ step_kernel(const __grid_constant__ ModelDev<T> M, const __grid_constant__ TaskD
         finite = finite && isfinite(q[i]) && isfinite(v[i]);
     }
     const double a0[2] = {(double)act.x, (double)act.y};
-    const double a_old[2] = {(double)S.a_prev[e], (double)S.a_prev[NE + e]};
+    const double a_old[2] = {(double)C(SL::AOLD), (double)C(SL::AOLD + 1)};
     double o[OS2R_MAX_OBS];
     const bool task_done = observe<N>(K, q, v, a_old, o);
     const double r = reward_fn(K.cfg, o, a0, a_old);
     const int D = K.cfg.obs_dim;
     int cause = task_done ? 1 : 0;
     if (!finite) cause |= 4;
-    const int steps = S.steps[e] + 1;
-    const double ret = S.ret[e] + r;
+    const int steps = __float_as_int_t<T>(C(SL::MISC)) + 1;
+    const double ret = __hiloint2double(__float_as_int_t<T>(C(SL::MISC + 2)), __float_as_int_t<T>(C(SL::MISC + 1))) + r;
     if (K.cfg.max_episode_steps > 0 && steps >= K.cfg.max_episode_steps) cause |= 2;
 
     reward[e] = (float)r;
@@ -165,7 +191,7 @@ step_kernel(const __grid_constant__ ModelDev<T> M, const __grid_constant__ TaskD
         atomicAdd(&stats->sum_length, (double)steps);
     }
     if (cause && (K.cfg.auto_reset || !finite)) {
-        reset_env_global<T, N, NC>(K, S, e, a_old, obs + e * D);
+        reset_idx = reset_env_global<T, N, NC>(K, S, e, a_old, obs + e * D);
     } else {
 #pragma unroll
         for (int i = 0; i < N; ++i) {
@@ -181,7 +207,7 @@ step_kernel(const __grid_constant__ ModelDev<T> M, const __grid_constant__ TaskD
         for (int k = 0; k < D; ++k) obs[e * D + k] = (float)o[k];
     }
     if (info) {
-        info[2 * e] = S.reset_id[e];
+        info[2 * e] = reset_idx;
         info[2 * e + 1] = cause;
     }
 }
