@@ -90,6 +90,12 @@ __device__ __forceinline__ void sincos_t(float x, float *s, float *c) { sincosf(
 __device__ __forceinline__ void sincos_t(double x, double *s, double *c) { sincos(x, s, c); }
 __device__ __forceinline__ float sqrt_t(float x) { return sqrtf(x); }
 __device__ __forceinline__ double sqrt_t(double x) { return sqrt(x); }
+// 1/sqrt(x) to ~1 ulp: MUFU.RSQ + one Newton step (shorter dependency chain than sqrtf followed by a division)
+__device__ __forceinline__ float rsqrt_t(float x) {
+    const float r = rsqrtf(x);
+    return fmaf(r, fmaf(-0.5f * x * r, r, 0.5f), r);
+}
+__device__ __forceinline__ double rsqrt_t(double x) { return 1.0 / sqrt(x); }
 __device__ __forceinline__ float rcp_t(float x) { return 1.0f / x; }
 __device__ __forceinline__ double rcp_t(double x) { return 1.0 / x; }
 __device__ __forceinline__ float fmin_t(float a, float b) { return fminf(a, b); }
@@ -101,11 +107,12 @@ __device__ __forceinline__ double fmax_t(double a, double b) { return fmax(a, b)
 // Deliberately NOT inlined: sincosf's range-reduction slow path is ~150 instructions, and the physics loop
 // calls this once per joint; one shared copy keeps the loop body inside the instruction cache.
 template <typename T>
-__device__ __noinline__ void joint_sincos(T hi, T lo, T *s_out, T *c_out) {
+struct SinCos { T s, c; };       // returned by value: stays in registers across the call (pointers would go via the stack)
+template <typename T>
+__device__ __noinline__ SinCos<T> joint_sincos(T hi, T lo) {
     T s, c;
     sincos_t(hi, &s, &c);
-    *s_out = s + lo * c;
-    *c_out = c - lo * s;
+    return SinCos<T>{s + lo * c, c - lo * s};
 }
 
 // bit-preserving int <-> T for parking integers in the T-typed shared-memory slots
@@ -257,8 +264,8 @@ __device__ __forceinline__ void physics_iteration(const ModelDev<T> &M, EnvRegs<
                     for (int c = 0; c < 3; ++c)
                         A[3 * r + c] = R[3 * r] * tR[c] + R[3 * r + 1] * tR[3 + c] + R[3 * r + 2] * tR[6 + c];
             }
-            T s, c;
-            joint_sincos(E.q_hi[i], sizeof(T) == 4 ? C(SL::QLO + i) : T(0), &s, &c);
+            const SinCos<T> sc = joint_sincos<T>(E.q_hi[i], sizeof(T) == 4 ? C(SL::QLO + i) : T(0));
+            const T s = sc.s, c = sc.c;
 #pragma unroll
             for (int r = 0; r < 3; ++r) {
                 const T a1 = A[3 * r + 1], a2 = A[3 * r + 2];
@@ -345,9 +352,8 @@ __device__ __forceinline__ void physics_iteration(const ModelDev<T> &M, EnvRegs<
             T d = Mm[j][j] + dadd[j];
 #pragma unroll
             for (int k = 0; k < j; ++k) d -= Lo[j][k] * Lo[j][k];
-            const T sd = sqrt_t(d);
-            const T rd = rcp_t(sd);
-            Lo[j][j] = sd;
+            const T rd = rsqrt_t(d);
+            Lo[j][j] = d * rd;
             Lrd[j] = rd;
 #pragma unroll
             for (int i = j + 1; i < N; ++i) {
