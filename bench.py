@@ -112,12 +112,12 @@ def cpu_reference_run(steps, warmup, envs_per_core=128, cores=None):
     orc = oracle.Oracle(cm.struct, cfg, N, seed=42, nthreads=cores)
     orc.reset()
     rng = np.random.RandomState(42)
-    acts = [rng.uniform(-1, 1, (N, 2)) for _ in range(8)]
     for i in range(warmup):
-        orc.step(acts[i % 8])
+        orc.step(rng.uniform(-1, 1, (N, 2)))
+    acts = [rng.uniform(-1, 1, (N, 2)) for _ in range(steps)]     # fresh actions every step, generated untimed
     t0 = time.perf_counter()
     for i in range(steps):
-        orc.step(acts[i % 8])
+        orc.step(acts[i])
     dt = time.perf_counter() - t0
     return dict(value=N * steps / dt, ms_per_step=dt / steps * 1e3, n_envs=N, cores=cores,
                 sample=f'{N} envs ({envs_per_core}/core) x {steps} env steps, fixed_hip + randomizers, fp64 C oracle, '
@@ -253,7 +253,7 @@ def main():
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_s = float(te[0])
     D = eng.obs_dim
-    h2d, d2h = N * 2 * 4, N * (D * 4 + 4 + 1)
+    h2d, d2h = N * 2 * 4, N * (D * 4 + 4 + 1 + 8)      # actions in; obs + reward + done + info[2] out
 
     # the path's only collective: reduce episode statistics over ranks (NCCL over NVLink)
     st = eng.stats()

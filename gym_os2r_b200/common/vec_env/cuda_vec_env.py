@@ -18,8 +18,8 @@ class LazyInfos(Sequence):
     """The per-env ``info`` dicts of a step, built on access: materialising 65 536 dicts per step
     would cost more than the physics. ``infos[i]`` / iteration / ``len`` behave like the reference's tuple."""
 
-    def __init__(self, names, reset_ids, done, terminal_obs, truncated):
-        self._names, self._rid, self._done, self._term, self._trunc = names, reset_ids, done, terminal_obs, truncated
+    def __init__(self, names, reset_ids, done, terminal_obs, cause):
+        self._names, self._rid, self._done, self._term, self._cause = names, reset_ids, done, terminal_obs, cause
 
     def __len__(self):
         return len(self._rid)
@@ -33,7 +33,7 @@ class LazyInfos(Sequence):
         if self._done[i]:
             if self._term is not None:
                 d['terminal_observation'] = self._term[i]
-            if self._trunc[i]:
+            if (int(self._cause[i]) & 3) == 2:       # ended by the TimeLimit only (gym: truncated = not done-by-task)
                 d['TimeLimit.truncated'] = True
         return d
 
@@ -75,7 +75,7 @@ class CudaVecEnv:
         if kind == 'host':
             # numpy in / numpy out through the C-ABI host entry point (pinned staging, H2D + kernel + D2H)
             obs, rew, done, term, info = self.runtime.engine.step_host(payload, want_terminal_obs=True, want_info=True)
-            return obs, rew, done, LazyInfos(names, info[:, 0], done, term, (info[:, 1] & 3) == 2)
+            return obs, rew, done, LazyInfos(names, info[:, 0], done, term, info[:, 1])
         obs, rew, done, info = payload
         if self.output == 'torch':
             return obs, rew, done, info
@@ -83,8 +83,8 @@ class CudaVecEnv:
         done_h = done.cpu().numpy()
         rid = info['reset_orientation'].cpu().numpy()
         term = info['terminal_observation'].cpu().numpy() if done_h.any() else None
-        trunc = info['TimeLimit.truncated'].cpu().numpy()
-        return obs.cpu().numpy(), rew.cpu().numpy(), done_h, LazyInfos(names, rid, done_h, term, trunc)
+        cause = info['cause'].cpu().numpy()
+        return obs.cpu().numpy(), rew.cpu().numpy(), done_h, LazyInfos(names, rid, done_h, term, cause)
 
     def step(self, actions):
         self.step_async(actions)

@@ -396,6 +396,13 @@ int32_t os2r_step(os2r_env *h, const float *actions_dev, float *obs_dev, float *
     return do_step(h, actions_dev, obs_dev, reward_dev, done_dev, terminal_obs_dev, info_dev, (cudaStream_t)stream);
 }
 
+// true when `p` is page-locked host memory the GPU can DMA to/from directly (cudaHostAlloc / cudaHostRegister)
+static bool is_pinned(const void *p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
+
 int32_t os2r_step_host(os2r_env *h, const float *actions, float *obs, float *reward, uint8_t *done,
                        float *terminal_obs, int32_t *info) {
     if (!h) return fail("os2r_step_host: null handle");
@@ -405,30 +412,34 @@ int32_t os2r_step_host(os2r_env *h, const float *actions, float *obs, float *rew
     const int64_t N = h->n;
     const int D = h->task.obs_dim;
     cudaStream_t st = h->host_stream;
-    memcpy(h->pin_actions, actions, N * 2 * sizeof(float));
-    CK(cudaMemcpyAsync(h->dev_actions, h->pin_actions, N * 2 * sizeof(float), cudaMemcpyHostToDevice, st));
+    // Pageable caller buffers are staged through the handle's pinned area (one extra host memcpy each way);
+    // page-locked caller buffers are DMA targets themselves.
+    const bool pa = is_pinned(actions), po = is_pinned(obs), pr = is_pinned(reward), pd = is_pinned(done);
+    const bool pt = terminal_obs && is_pinned(terminal_obs), pi = info && is_pinned(info);
+    if (!pa) memcpy(h->pin_actions, actions, N * 2 * sizeof(float));
+    CK(cudaMemcpyAsync(h->dev_actions, pa ? actions : h->pin_actions, N * 2 * sizeof(float), cudaMemcpyHostToDevice, st));
     if (do_step(h, h->dev_actions, h->dev_obs, h->dev_reward, h->dev_done, terminal_obs ? h->dev_term : nullptr,
                 info ? h->dev_info : nullptr, st)) return 1;
-    CK(cudaMemcpyAsync(h->pin_obs, h->dev_obs, N * D * sizeof(float), cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(h->pin_reward, h->dev_reward, N * sizeof(float), cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(h->pin_done, h->dev_done, N, cudaMemcpyDeviceToHost, st));
-    if (info) CK(cudaMemcpyAsync(h->pin_info, h->dev_info, N * 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(po ? obs : h->pin_obs, h->dev_obs, N * D * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(pr ? reward : h->pin_reward, h->dev_reward, N * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(pd ? done : h->pin_done, h->dev_done, N, cudaMemcpyDeviceToHost, st));
+    if (info) CK(cudaMemcpyAsync(pi ? info : h->pin_info, h->dev_info, N * 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
-    memcpy(obs, h->pin_obs, N * D * sizeof(float));
-    memcpy(reward, h->pin_reward, N * sizeof(float));
-    memcpy(done, h->pin_done, N);
-    if (info) memcpy(info, h->pin_info, N * 2 * sizeof(int32_t));
+    if (!po) memcpy(obs, h->pin_obs, N * D * sizeof(float));
+    if (!pr) memcpy(reward, h->pin_reward, N * sizeof(float));
+    if (!pd) memcpy(done, h->pin_done, N);
+    if (info && !pi) memcpy(info, h->pin_info, N * 2 * sizeof(int32_t));
     if (terminal_obs) {
         // The terminal observation differs from `obs` only for envs that finished an episode, so it is
         // fetched lazily: a second D2H only on steps where some env is done (rare: episodes are long).
         bool any_done = false;
-        for (int64_t e = 0; e < N && !any_done; ++e) any_done = h->pin_done[e] != 0;
+        for (int64_t e = 0; e < N && !any_done; ++e) any_done = done[e] != 0;
         if (any_done) {
-            CK(cudaMemcpyAsync(h->pin_term, h->dev_term, N * D * sizeof(float), cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(pt ? terminal_obs : h->pin_term, h->dev_term, N * D * sizeof(float), cudaMemcpyDeviceToHost, st));
             CK(cudaStreamSynchronize(st));
-            memcpy(terminal_obs, h->pin_term, N * D * sizeof(float));
+            if (!pt) memcpy(terminal_obs, h->pin_term, N * D * sizeof(float));
         } else {
-            memcpy(terminal_obs, h->pin_obs, N * D * sizeof(float));
+            memcpy(terminal_obs, obs, N * D * sizeof(float));
         }
     }
     return 0;

@@ -2,6 +2,7 @@
 work is done by libos2r.so. This is plumbing, not a fallback: every method raises if the CUDA
 library or a CUDA device is missing."""
 import ctypes as C
+import sys
 
 import numpy as np
 import torch
@@ -45,6 +46,7 @@ class Engine:
         self.done_u8 = torch.zeros(N, dtype=torch.uint8, **kw)
         self.terminal_obs = torch.zeros((N, D), dtype=torch.float32, **kw)
         self.info = torch.zeros((N, 2), dtype=torch.int32, **kw)
+        self._host_pool = {}
 
     # ------------------------------------------------------------------ lifecycle
     def close(self):
@@ -87,17 +89,32 @@ class Engine:
             C.c_void_p(self.info.data_ptr()) if want_info else None, self._stream()), self.lib)
         return self.obs, self.reward, self.done_u8, self.info
 
+    def _host_array(self, key, shape, dtype):
+        """A page-locked numpy array for a step_host output. Arrays are recycled ONLY when the caller holds no
+        reference to them any more (refcount check), so results are never overwritten behind the user's back,
+        yet the steady state allocates nothing (fresh 2 MB arrays per step cost ~1 ms in page faults) and the
+        GPU DMAs straight into the array the user receives (no staging copy)."""
+        pool = self._host_pool.setdefault(key, [])
+        for k in range(len(pool)):
+            if sys.getrefcount(pool[k]) <= 2:      # the pool's reference + getrefcount's argument
+                return pool[k]
+        t = torch.empty(shape, dtype=dtype).pin_memory()
+        arr = t.numpy()                            # keeps `t` alive through .base
+        if len(pool) < 64:
+            pool.append(arr)
+        return arr
+
     def step_host(self, actions: np.ndarray, want_terminal_obs: bool = False, want_info: bool = False):
-        """numpy in / numpy out (fresh arrays each call): H2D + kernel + D2H inside os2r_step_host."""
+        """numpy in / numpy out: H2D + kernel + D2H inside os2r_step_host. Returned arrays belong to the caller."""
         a = np.ascontiguousarray(actions, dtype=np.float32)
         if a.shape != (self.n_envs, 2):
             raise ValueError(f'actions must have shape ({self.n_envs}, 2), got {a.shape}')
         N, D = self.n_envs, self.obs_dim
-        obs = np.empty((N, D), dtype=np.float32)
-        rew = np.empty(N, dtype=np.float32)
-        done = np.empty(N, dtype=np.bool_)
-        term = np.empty((N, D), dtype=np.float32) if want_terminal_obs else None
-        info = np.empty((N, 2), dtype=np.int32) if want_info else None
+        obs = self._host_array('obs', (N, D), torch.float32)
+        rew = self._host_array('rew', (N,), torch.float32)
+        done = self._host_array('done', (N,), torch.bool)
+        term = self._host_array('term', (N, D), torch.float32) if want_terminal_obs else None
+        info = self._host_array('info', (N, 2), torch.int32) if want_info else None
         p = lambda x: x.ctypes.data_as(C.c_void_p) if x is not None else None
         _capi.check(self.lib.os2r_step_host(self.handle, p(a), p(obs), p(rew), p(done), p(term), p(info)), self.lib)
         return obs, rew, done, term, info

@@ -209,7 +209,7 @@ def test_shard_range_and_lazy_infos():
     assert [shard_range(10, r, 4) for r in range(4)] == [(0, 3), (3, 3), (6, 2), (8, 2)]
     assert shard_range(1 << 20, 7, 8) == (7 * 131072, 131072)
     infos = LazyInfos(['stand', 'lay'], np.array([0, 1, 1]), np.array([False, True, True]),
-                      np.arange(6.0).reshape(3, 2), np.array([False, False, True]))
+                      np.arange(6.0).reshape(3, 2), np.array([0, 1, 2]))
     assert len(infos) == 3 and infos[0] == {'reset_orientation': 'stand'}
     assert infos[2]['TimeLimit.truncated'] and infos[1]['terminal_observation'].tolist() == [2.0, 3.0]
     assert [i['reset_orientation'] for i in infos] == ['stand', 'lay', 'lay']
