@@ -275,6 +275,19 @@ def main():
         except Exception:
             pass
         hbm_peak = peaks.get('hbm_gbs', 6650.0)
+        # DRAM traffic per launch of the step kernel from the committed `ncu --set full` capture of this workload
+        # (profiles/r1_step_kernel_final_steady.txt: dram__bytes_read.sum + dram__bytes_write.sum), else null.
+        traffic = None
+        try:
+            tot = 0.0
+            unit_scale = {'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}
+            for ln in open(os.path.join(ROOT, 'profiles', 'r1_step_kernel_final_steady.txt')):
+                if ln.startswith('dram__bytes_read.sum') or ln.startswith('dram__bytes_write.sum'):
+                    _, val, unit = ln.split()
+                    tot += float(val) * unit_scale[unit]
+            traffic = tot or None
+        except Exception:
+            pass
         line = dict(base, value=value, ms_per_step=total_ms / K, dtype='f32',
                     config={'workload': workload, 'envs_per_gpu': N, 'n_dof': N_DOF, 'obs_dim': OBS_DIM,
                             'pgs_iters': int(rt._compiled.struct.pgs_iters),
@@ -287,7 +300,8 @@ def main():
                          'd2h_bytes_per_step': d2h, 'steps': K2, 'api': 'make_mp_envs(...).step(numpy) -> os2r_step_host'},
                     gpu_launches=int(launches),
                     roofline={'bound': 'fp32', 'achieved': achieved_tf, 'peak': fp32_peak, 'unit': 'TFLOP/s',
-                              'frac': achieved_tf / fp32_peak if fp32_peak else None, 'traffic': None,
+                              'frac': achieved_tf / fp32_peak if fp32_peak else None, 'traffic': traffic,
+                              'traffic_note': 'bytes per launch, ncu capture in profiles/ (algorithmic: %d)' % (N * B),
                               'kernel': f'step_kernel<float,{N_DOF},3>', 'flop_per_env_step': F,
                               'peak_source': 'FFMA microbenchmark measured in this run (os2r_measure_fp32_peak); '
                                              'MEASURED_PEAKS.json has no fp32 entry',

@@ -137,6 +137,9 @@ class CudaRuntime(Env):
 
     def step(self, action):
         eng = self.engine
+        custom = self._cfg.reward_id == _capi.REWARD_CUSTOM
+        if not self.batched and not custom:
+            return self._step_single(action)
         if self.batched:
             a = action if torch.is_tensor(action) else torch.as_tensor(np.asarray(action, dtype=np.float32), device=eng.device)
             a = a.to(device=eng.device, dtype=torch.float32).reshape(self.num_envs, 2).contiguous()
@@ -146,7 +149,7 @@ class CudaRuntime(Env):
                 warnings.warn('The action does not belong to the action space')
             a = torch.as_tensor(arr.astype(np.float32), device=eng.device).reshape(1, 2)
         obs, reward, done_u8, info_t = eng.step(a)
-        if self._cfg.reward_id == _capi.REWARD_CUSTOM:
+        if custom:
             # user-defined RewardBase subclass: batched torch evaluation on the device
             prev = self._prev_actions if self._prev_actions is not None else torch.zeros_like(a)
             src = eng.terminal_obs if self._cfg.auto_reset else obs
@@ -162,16 +165,30 @@ class CudaRuntime(Env):
             return obs, reward, self._out['done'], info
         torch.cuda.synchronize(eng.device)
         info_h = info_t[0].cpu().numpy()
-        a_h = a[0].double().cpu().numpy()
-        self.task.action_history.appendleft(a_h)
-        self.task.current_reset_orientation = self.task.reset_positions[int(info_h[0])]
+        self.task.action_history.appendleft(a[0].double().cpu().numpy())
+        return self._single_result(obs[0].double().cpu().numpy(), float(reward[0].item()), bool(done_u8[0].item()), info_h)
+
+    def _step_single(self, action):
+        """The reference's single-env call shape: one C-ABI host call (H2D + kernel + D2H), no torch round trips."""
+        arr = np.asarray(action, dtype=np.float64).reshape(2)
+        if not self.action_space.contains(arr):
+            warnings.warn('The action does not belong to the action space')
+        obs, rew, done, _, info = self.engine.step_host(arr.astype(np.float32).reshape(1, 2), False, True)
+        self.task.action_history.appendleft(arr.copy())
+        self._out = {'obs_h': obs[0].astype(np.float64), 'reward_h': float(rew[0]), 'done_h': bool(done[0])}
+        return self._single_result(self._out['obs_h'], self._out['reward_h'], self._out['done_h'], info[0])
+
+    def _single_result(self, obs, reward, done, info_row):
+        self.task.current_reset_orientation = self.task.reset_positions[int(info_row[0])]
         info = self.task.get_info()
-        if (int(info_h[1]) & 3) == 2:
+        if (int(info_row[1]) & 3) == 2:
             info['TimeLimit.truncated'] = True
-        return (obs[0].double().cpu().numpy(), float(reward[0].item()), bool(done_u8[0].item()), info)
+        return obs, reward, done, info
 
     def _last(self, key):
         """Outputs of the most recent fused step (what the Task's get_* methods return)."""
+        if key + '_h' in self._out:
+            return self._out[key + '_h']
         if key not in self._out:
             raise RuntimeError('no step has been executed yet')
         v = self._out[key]
