@@ -170,7 +170,9 @@ int ensure_host_io(os2r_env *h) {
     if (h->host_io_ready) return 0;
     const int64_t N = h->n;
     const int D = h->task.obs_dim;
-    CK(cudaStreamCreateWithFlags(&h->host_stream, cudaStreamNonBlocking));
+    // a BLOCKING stream: implicitly ordered after work on the legacy default stream (what torch uses by default),
+    // so a reset / device-buffer step enqueued there cannot race with a following host-buffer step
+    CK(cudaStreamCreate(&h->host_stream));
     CK(cudaMallocHost(&h->pin_actions, N * 2 * sizeof(float)));
     CK(cudaMallocHost(&h->pin_obs, N * D * sizeof(float)));
     CK(cudaMallocHost(&h->pin_term, N * D * sizeof(float)));
