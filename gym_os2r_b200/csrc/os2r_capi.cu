@@ -503,13 +503,15 @@ int32_t os2r_kernel_info(const os2r_env *h, int32_t *block_threads, int32_t *gri
     if (!h) return fail("os2r_kernel_info: null handle");
     DeviceGuard guard(h->device);
     cudaFuncAttributes a;
-    cudaError_t e = h->precision == 32 ? step_kernel_attributes<float>(h->model.n_dof, &a)
-                                       : step_kernel_attributes<double>(h->model.n_dof, &a);
+    int resident = 0;
+    cudaError_t e = h->precision == 32 ? step_kernel_attributes<float>(h->model.n_dof, &a, &resident)
+                                       : step_kernel_attributes<double>(h->model.n_dof, &a, &resident);
     if (e != cudaSuccess) return fail("cudaFuncGetAttributes failed: %s", cudaGetErrorString(e));
     if (block_threads) *block_threads = OS2R_BLOCK;
     if (grid_blocks) *grid_blocks = (int32_t)((h->n + OS2R_BLOCK - 1) / OS2R_BLOCK);
     if (regs_per_thread) *regs_per_thread = a.numRegs;
-    if (local_bytes_per_thread) *local_bytes_per_thread = (int32_t)a.localSizeBytes;
+    // local bytes in the low 20 bits, resident blocks per SM (occupancy API) above them
+    if (local_bytes_per_thread) *local_bytes_per_thread = (int32_t)a.localSizeBytes | (resident << 20);
     return 0;
 }
 

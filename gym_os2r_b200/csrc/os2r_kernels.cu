@@ -269,8 +269,13 @@ cudaError_t launch_init(const TaskDev &K, const StateDev<T> &S, double nominal_g
 }
 
 template <typename T>
-cudaError_t step_kernel_attributes(int n_dof, cudaFuncAttributes *attr) {
-    OS2R_DISPATCH_N(n_dof, return cudaFuncGetAttributes(attr, step_kernel<T, N_, OS2R_NC>));
+cudaError_t step_kernel_attributes(int n_dof, cudaFuncAttributes *attr, int *blocks_per_sm) {
+    OS2R_DISPATCH_N(n_dof, {
+        cudaError_t e = cudaFuncGetAttributes(attr, step_kernel<T, N_, OS2R_NC>);
+        if (e != cudaSuccess) return e;
+        return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, step_kernel<T, N_, OS2R_NC>, OS2R_BLOCK,
+                                                             ColdSlots<N_, OS2R_NC>::COUNT * OS2R_BLOCK * sizeof(T));
+    });
     return cudaSuccess;
 }
 
@@ -286,7 +291,7 @@ cudaError_t launch_fma_peak(float *out, int blocks, int iters, cudaStream_t stre
     template cudaError_t launch_reset<T>(int, int, const TaskDev &, const StateDev<T> &, const uint8_t *,     \
                                          float *, cudaStream_t);                                              \
     template cudaError_t launch_init<T>(const TaskDev &, const StateDev<T> &, double, cudaStream_t);          \
-    template cudaError_t step_kernel_attributes<T>(int, cudaFuncAttributes *);
+    template cudaError_t step_kernel_attributes<T>(int, cudaFuncAttributes *, int *);
 OS2R_INSTANTIATE(float)
 OS2R_INSTANTIATE(double)
 

@@ -25,7 +25,7 @@ cudaError_t launch_reset(int n_dof, int n_contacts, const TaskDev &K, const Stat
 template <typename T>
 cudaError_t launch_init(const TaskDev &K, const StateDev<T> &S, double nominal_gz, cudaStream_t stream);
 template <typename T>
-cudaError_t step_kernel_attributes(int n_dof, cudaFuncAttributes *attr);
+cudaError_t step_kernel_attributes(int n_dof, cudaFuncAttributes *attr, int *blocks_per_sm);
 cudaError_t launch_fma_peak(float *out, int blocks, int iters, cudaStream_t stream);
 
 }  // namespace os2r
