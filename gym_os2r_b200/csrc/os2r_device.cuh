@@ -490,30 +490,27 @@ __device__ __forceinline__ void physics_iteration(const ModelDev<T> &M, EnvRegs<
     // ---- projected Gauss-Seidel sweeps in whitened coordinates -------------------------------------------
     // Row update with relative CFM c on the diagonal A(1+c):
     //   lam' = clamp(lam - (G.z - target + c*A*lam) / (A(1+c))) = clamp(lam*(1-k) - (G.z - target)*inv),
-    //   k = c/(1+c), inv = 1/(A(1+c)) precomputed per row.
+    //   1-k = 1/(1+c), inv = 1/(A(1+c)) precomputed per row.
     // Early exit: a sweep that changes no impulse of any lane of the warp is a fixed point, so the remaining
     // sweeps would reproduce it bit for bit — skipping them is exact (typical: saturated joint friction, no contact).
-    const T kj = M.cfm_joint / (T(1) + M.cfm_joint), kc = M.cfm_contact / (T(1) + M.cfm_contact);
+    const T kj1 = T(1) / (T(1) + M.cfm_joint), kc1 = T(1) / (T(1) + M.cfm_contact);   // 1 - k
 #pragma unroll 1
     for (int it = 0; it < M.pgs_iters; ++it) {
-        bool changed = false;
+        T chg = 0;       // max |delta lambda| of this sweep (exactly 0 <=> fixed point)
 #pragma unroll
         for (int r = 0; r < N; ++r) {
-            if (jact[r]) {
-                const T lam = C(SL::LAM + r), lim = C(SL::FRIC + r);
-                T w = bj[r];
+            // branch-free: a row without friction has bound 0, so its impulse stays 0 and the update adds 0
+            const T lam = C(SL::LAM + r), lim = C(SL::FRIC + r);
+            T w = bj[r];
 #pragma unroll
-                for (int k = r; k < N; ++k) w += Gj[r][k] * z[k];
-                T nl = lam - (kj * lam + w * Aj[r]);
-                nl = fmax_t(-lim, fmin_t(lim, nl));
-                const T dl = nl - lam;
-                if (dl != T(0)) {
-                    changed = true;
+            for (int k = r; k < N; ++k) w += Gj[r][k] * z[k];
+            T nl = lam * kj1 - w * Aj[r];
+            nl = fmax_t(-lim, fmin_t(lim, nl));
+            const T dl = nl - lam;
 #pragma unroll
-                    for (int k = r; k < N; ++k) z[k] += Gj[r][k] * dl;
-                    C(SL::LAM + r) = nl;
-                }
-            }
+            for (int k = r; k < N; ++k) z[k] += Gj[r][k] * dl;
+            C(SL::LAM + r) = nl;
+            chg = fmax_t(chg, dl < T(0) ? -dl : dl);
         }
 #pragma unroll
         for (int c = 0; c < NC; ++c) {
@@ -526,23 +523,21 @@ __device__ __forceinline__ void physics_iteration(const ModelDev<T> &M, EnvRegs<
                     T w = bc[c][d];
 #pragma unroll
                     for (int k = 0; k < N; ++k) w += Gc[c][d][k] * z[k];
-                    T nl = lam - (kc * lam + w * Ac[c][d]);
+                    T nl = lam * kc1 - w * Ac[c][d];
                     if (d == 0) { nl = fmax_t(nl, T(0)); ln = nl; }
                     else {
                         const T lim = C(SL::MU + c) * ln;
                         nl = fmax_t(-lim, fmin_t(lim, nl));
                     }
                     const T dl = nl - lam;
-                    if (dl != T(0)) {
-                        changed = true;
 #pragma unroll
-                        for (int k = 0; k < N; ++k) z[k] += Gc[c][d][k] * dl;
-                        C(SL::LAM + r) = nl;
-                    }
+                    for (int k = 0; k < N; ++k) z[k] += Gc[c][d][k] * dl;
+                    C(SL::LAM + r) = nl;
+                    chg = fmax_t(chg, dl < T(0) ? -dl : dl);
                 }
             }
         }
-        if (!__any_sync(__activemask(), changed)) break;
+        if (!__any_sync(__activemask(), chg != T(0))) break;
     }
     // ---- v = v* + L^-T z ; q += dt v  (TwoSum-compensated (hi, lo) pairs in fp32) --------------------------
     {
