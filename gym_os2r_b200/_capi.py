@@ -13,7 +13,7 @@ MAX_OBS = 12
 MAX_RESETS = 8
 MAX_ROWS = MAX_DOF + 3 * MAX_CONTACTS
 N_ROLES = 5
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 ROLE_HIP, ROLE_KNEE, ROLE_PITCH, ROLE_YAW, ROLE_BOOM_CONNECTOR = range(5)
 ROLE_OF_JOINT = {
@@ -111,7 +111,7 @@ SYMBOLS = {
     'os2r_obs_dim': (_i32, [_vp]),
     'os2r_kernel_launches': (C.c_int64, [_vp]),
     'os2r_kernel_info': (_i32, [_vp, C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32),
-                                C.POINTER(_i32)]),
+                                C.POINTER(_i32), C.POINTER(_i32)]),
     'os2r_measure_fp32_peak': (_i32, [_i32, C.POINTER(_f64), C.POINTER(_f64)]),
 }
 

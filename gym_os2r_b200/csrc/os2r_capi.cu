@@ -499,7 +499,7 @@ int32_t os2r_obs_dim(const os2r_env *h) { return h ? h->task.obs_dim : 0; }
 int64_t os2r_kernel_launches(const os2r_env *h) { return h ? h->launches : 0; }
 
 int32_t os2r_kernel_info(const os2r_env *h, int32_t *block_threads, int32_t *grid_blocks, int32_t *regs_per_thread,
-                         int32_t *local_bytes_per_thread) {
+                         int32_t *local_bytes_per_thread, int32_t *resident_blocks_per_sm) {
     if (!h) return fail("os2r_kernel_info: null handle");
     DeviceGuard guard(h->device);
     cudaFuncAttributes a;
@@ -510,8 +510,8 @@ int32_t os2r_kernel_info(const os2r_env *h, int32_t *block_threads, int32_t *gri
     if (block_threads) *block_threads = OS2R_BLOCK;
     if (grid_blocks) *grid_blocks = (int32_t)((h->n + OS2R_BLOCK - 1) / OS2R_BLOCK);
     if (regs_per_thread) *regs_per_thread = a.numRegs;
-    // local bytes in the low 20 bits, resident blocks per SM (occupancy API) above them
-    if (local_bytes_per_thread) *local_bytes_per_thread = (int32_t)a.localSizeBytes | (resident << 20);
+    if (local_bytes_per_thread) *local_bytes_per_thread = (int32_t)a.localSizeBytes;
+    if (resident_blocks_per_sm) *resident_blocks_per_sm = resident;
     return 0;
 }
 

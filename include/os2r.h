@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define OS2R_ABI_VERSION 3
+#define OS2R_ABI_VERSION 4
 
 #define OS2R_MAX_DOF 5
 #define OS2R_MAX_CONTACTS 4
@@ -201,10 +201,11 @@ int32_t os2r_stats_read(os2r_env *env, os2r_stats *out, int32_t clear);
 int64_t os2r_num_envs(const os2r_env *env);
 int32_t os2r_obs_dim(const os2r_env *env);
 int64_t os2r_kernel_launches(const os2r_env *env); /* kernels launched by this handle so far */
-/* Launch geometry and static resource use of the step kernel (for the roofline report).
- * *local_bytes_per_thread: low 20 bits = local memory bytes, bits 20+ = resident blocks per SM (occupancy API). */
+/* Launch geometry and static resource use of the step kernel (for the roofline report);
+ * resident_blocks_per_sm comes from the CUDA occupancy API. Any out pointer may be NULL. */
 int32_t os2r_kernel_info(const os2r_env *env, int32_t *block_threads, int32_t *grid_blocks,
-                         int32_t *regs_per_thread, int32_t *local_bytes_per_thread);
+                         int32_t *regs_per_thread, int32_t *local_bytes_per_thread,
+                         int32_t *resident_blocks_per_sm);
 /* fp32 FMA-pipe peak microbenchmark on the handle's device: returns TFLOP/s (2 flop per FMA)
  * measured with CUDA events (MEASURED_PEAKS.json has no fp32 entry). */
 int32_t os2r_measure_fp32_peak(int32_t device, double *tflops_out, double *sm_clock_mhz_out);

@@ -405,3 +405,84 @@ def test_contact_rollout_statistics_match_oracle():
     assert np.abs(td_g - td_o)[landed].max() <= 2, (td_g[landed], td_o[landed])
     assert abs(ret_g.mean() - ret_o.mean()) <= 0.02 * max(1.0, abs(ret_o.mean()))
     eng.close()
+
+
+def test_small_oscillation_frequencies_match_linearised_model():
+    """Oracle-independent physics check (SURVEY.md section 8c iii): `fixed` mode with the boom pitch locked at 0.5 rad
+    by a large joint friction, leg undamped and frictionless. Released along each normal mode of the linearised leg
+    M_leg(q0) x'' + K_leg x = 0 (M from an independent numpy Lagrangian mass matrix, K = Hessian of the potential by
+    finite differences), the kernel must oscillate at the analytic modal frequency."""
+    from scipy.linalg import eigh
+    from gym_os2r_b200.models import compiler
+    task, cm, cfg = make_config('fixed', reward='BalancingV1')
+    m = cm.struct
+    n = m.n_dof
+    ip, leg = cm.dof_of('planarizer_pitch_joint'), [cm.dof_of('hip_joint'), cm.dof_of('knee_joint')]
+    pitch = 0.5
+
+    def full(x):
+        q = np.zeros(n)
+        q[ip] = pitch
+        q[leg] = x
+        return q
+
+    def potential(x):
+        Rs, ps, _ = compiler.forward_kinematics(m, full(x))
+        return sum(-m.mass[b] * m.gravity_z * (ps[b] + Rs[b] @ np.array(m.com[b][:]))[2] for b in range(n))
+
+    def mass_matrix(x):
+        Rs, ps, _ = compiler.forward_kinematics(m, full(x))
+        M = np.zeros((n, n))
+        axes = [((Rs[i - 1] if i else np.eye(3)) @ np.array(m.tree_R[i][:]).reshape(3, 3))[:, m.axis[i]] for i in range(n)]
+        for b in range(n):
+            c = ps[b] + Rs[b] @ np.array(m.com[b][:])
+            t = m.inertia[b]
+            Iw = Rs[b] @ np.array([[t[0], t[3], t[4]], [t[3], t[1], t[5]], [t[4], t[5], t[2]]]) @ Rs[b].T
+            Jv = np.stack([np.cross(axes[j], c - ps[j]) if j <= b else np.zeros(3) for j in range(n)], 1)
+            Jw = np.stack([axes[j] if j <= b else np.zeros(3) for j in range(n)], 1)
+            M += m.mass[b] * Jv.T @ Jv + Jw.T @ Iw @ Jw
+        return M[np.ix_(leg, leg)]
+
+    def grad(x, h=1e-6):
+        return np.array([(potential(x + h * e) - potential(x - h * e)) / (2 * h) for e in np.eye(2)])
+
+    def hess(x, h=1e-4):
+        return np.array([(grad(x + h * e) - grad(x - h * e)) / (2 * h) for e in np.eye(2)])
+    # hanging equilibrium of the leg: try a few starts, keep the one with a positive-definite Hessian
+    x0 = None
+    for start in ([0.0, 0.0], [1.57, 0.0], [-1.57, 0.0], [3.14, 0.0]):
+        x = np.array(start)
+        for _ in range(40):
+            x = x - np.linalg.solve(hess(x), grad(x))
+        if np.linalg.eigvalsh(hess(x)).min() > 1e-3:
+            x0 = x
+            break
+    assert x0 is not None, 'no stable equilibrium found'
+    K, Mleg = hess(x0), mass_matrix(x0)
+    w2, modes = eigh(K, Mleg)
+    eng = Engine(cm, cfg, 2, precision=32)
+    p = eng.get_params()
+    p[:, n:3 * n] = 0.0                       # no damping, no friction ...
+    p[:, 2 * n + ip] = 100.0                  # ... except a friction lock on the boom pitch
+    eng.set_params(p)
+    st = np.zeros((2, eng.state_width))
+    for k in range(2):
+        st[k, :n] = full(x0 + 2e-3 * modes[:, k] / np.abs(modes[:, k]).max())
+    eng.set_state(st)
+    T = 3300                                   # modal periods are 1.06 s and 0.56 s; one env step = 1 ms
+    a = torch.zeros((2, 2), device='cuda')
+    hist = np.zeros((T, 2))
+    for t in range(T):
+        eng.step(a)
+        s = eng.get_state()
+        for k in range(2):
+            hist[t, k] = (s[k, leg] - x0) @ (Mleg @ modes[:, k])      # modal coordinate
+        assert np.abs(s[:, ip] - pitch).max() < 1e-6 and np.abs(s[:, n + ip]).max() < 1e-6   # the lock holds
+    for k in range(2):
+        x = hist[:, k]
+        up = np.nonzero((x[:-1] < 0) & (x[1:] >= 0))[0]
+        assert len(up) >= 3, (k, len(up))
+        tz = up + x[up] / (x[up] - x[up + 1])         # interpolated zero crossings; env step = 1 ms
+        period = np.diff(tz).mean() * 1e-3
+        assert period == pytest.approx(2 * np.pi / np.sqrt(w2[k]), rel=3e-3), (k, period, 2 * np.pi / np.sqrt(w2[k]))
+    eng.close()
