@@ -342,6 +342,7 @@ __device__ __forceinline__ void physics_iteration(const ModelDev<T> &M, EnvRegs<
             }
         }
     }
+    __syncthreads();   // second phase-alignment point per iteration (see the note at the physics loop)
     // ---- Cholesky of M (and of M + dt*D when any joint is damped); qdd; v* = v + dt*qdd ------------------
     T L[N][N];       // Cholesky factor of the plain M (lower); Ld = reciprocal diagonal
     T Ld[N];

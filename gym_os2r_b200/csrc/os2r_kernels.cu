@@ -93,9 +93,12 @@ step_kernel(const __grid_constant__ ModelDev<T> M, const __grid_constant__ TaskD
             const float *__restrict__ actions, float *__restrict__ obs, float *__restrict__ reward,
             uint8_t *__restrict__ done, float *__restrict__ term_obs, int32_t *__restrict__ info,
             StatsDev *stats) {
-    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t NE = S.n_envs;
-    if (e >= NE) return;
+    // Threads past the end of the batch (last block only) shadow the last env instead of exiting, so that the
+    // block-wide barriers inside the physics loop stay legal; they leave before anything is written.
+    const int64_t e_raw = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = e_raw < NE;
+    const int64_t e = valid ? e_raw : NE - 1;
     using SL = ColdSlots<N, NC>;
     constexpr int ROWS = SL::ROWS;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -153,7 +156,13 @@ step_kernel(const __grid_constant__ ModelDev<T> M, const __grid_constant__ TaskD
     C(SL::MISC + 2) = __int_as_float_t<T>(__double2hiint(ret_in));
 
 #pragma unroll 1
-    for (int s = 0; s < M.substeps; ++s) physics_iteration<T, N, NC, Cold<T, OS2R_BLOCK>>(M, E, C);
+    for (int s = 0; s < M.substeps; ++s) {
+        // Keep the block's warps in phase: all warps of an SM run the same ~45 KB loop body, and warps that drift
+        // apart thrash the 32 KB instruction cache (`no_instruction` was a top stall; measured -3..4 % step time).
+        __syncthreads();
+        physics_iteration<T, N, NC, Cold<T, OS2R_BLOCK>>(M, E, C);
+    }
+    if (!valid) return;
 
     // ---- epilogue (fp64, once per env step) --------------------------------------------------------
     double q[N], v[N];

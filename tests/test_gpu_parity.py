@@ -486,3 +486,30 @@ def test_small_oscillation_frequencies_match_linearised_model():
         period = np.diff(tz).mean() * 1e-3
         assert period == pytest.approx(2 * np.pi / np.sqrt(w2[k]), rel=3e-3), (k, period, 2 * np.pi / np.sqrt(w2[k]))
     eng.close()
+
+
+def test_dart_golden_trajectories_if_present():
+    """Real-reference parity (BASELINE.json north_star tolerances) against trajectories recorded with
+    tools/record_dart_golden.py on a machine that has gym-ignition + DART. No such recording can be made in this
+    environment, so the test reports that physics parity is oracle-only and skips."""
+    import glob
+    import os
+    files = sorted(glob.glob(os.path.join(os.path.dirname(__file__), 'golden', 'dart_*.npz')))
+    if not files:
+        pytest.skip('DART golden absent - oracle-only parity (record with tools/record_dart_golden.py)')
+    for f in files:
+        g = np.load(f, allow_pickle=True)
+        task, cm, cfg = make_config(str(g['task_mode']), reward='BalancingV1', reset_positions=(str(g['reset']),))
+        acts, q_ref, qd_ref = g['actions'], g['q'], g['qd']          # [T, E, 2], [T, E, nj], [T, E, nj]
+        T, E = acts.shape[:2]
+        eng = Engine(cm, cfg, E, precision=32)
+        eng.reset()
+        order = [cm.dof_of(str(n)) for n in g['joint_names']]
+        worst_q = worst_v = 0.0
+        for t in range(T):
+            eng.step(torch.as_tensor(acts[t].astype(np.float32), device='cuda'))
+            s = eng.get_state()
+            worst_q = max(worst_q, np.abs(s[:, order] - q_ref[t]).max())
+            worst_v = max(worst_v, np.abs(s[:, [cm.n_dof + d for d in order]] - qd_ref[t]).max())
+        eng.close()
+        assert worst_q <= 1e-4 and worst_v <= 1e-3, (f, worst_q, worst_v)
