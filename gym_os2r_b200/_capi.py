@@ -13,7 +13,7 @@ MAX_OBS = 12
 MAX_RESETS = 8
 MAX_ROWS = MAX_DOF + 3 * MAX_CONTACTS
 N_ROLES = 5
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 ROLE_HIP, ROLE_KNEE, ROLE_PITCH, ROLE_YAW, ROLE_BOOM_CONNECTOR = range(5)
 ROLE_OF_JOINT = {
@@ -44,7 +44,7 @@ class Model(C.Structure):
         ('contact_pos', (_f64 * 3) * MAX_CONTACTS), ('contact_radius', _f64 * MAX_CONTACTS),
         ('contact_mu', _f64 * MAX_CONTACTS),
         ('gravity_z', _f64), ('dt', _f64), ('erp', _f64), ('max_erv', _f64),
-        ('cfm_contact', _f64), ('cfm_joint', _f64), ('max_torque', _f64 * 2),
+        ('cfm_contact', _f64), ('cfm_joint', _f64), ('max_torque', _f64 * 2), ('pgs_tol', _f64),
     ]
 
 

@@ -103,6 +103,10 @@ void build_model_dev(const os2r_model &m, ModelDev<T> &d) {
     d.knee_dof = m.role_dof[OS2R_ROLE_KNEE];
     d.substeps = m.substeps;
     d.pgs_iters = m.pgs_iters;
+    d.pgs_tol2 = (T)(m.pgs_tol * m.pgs_tol);
+    // lane-sorting hint: a proxy within this clearance may touch down during the next env step
+    const char *margin = getenv("OS2R_SORT_MARGIN");
+    d.sort_margin = (T)(margin ? atof(margin) : 0.002);
     d.any_damping = 0;
     for (int i = 0; i < m.n_dof; ++i) if (m.damping[i] != 0.0) d.any_damping = 1;
 }
@@ -128,7 +132,10 @@ struct os2r_env {
     uint32_t *episode = nullptr;
     int32_t *reset_id = nullptr;
     double *ret = nullptr;
+    uint8_t *cls = nullptr;
     StatsDev *stats = nullptr;
+    int sm_count = 0;
+    int block = OS2R_BLOCK;          // threads per block of the step kernel for this batch size
     StateDev<float> s32;
     StateDev<double> s64;
     // host staging for os2r_step_host
@@ -157,7 +164,7 @@ void carve(os2r_env *h, StateDev<T> &S) {
     S.lam = take(h->rows); S.a_prev = take(2);
     S.mass_scale = take(n); S.damping = take(n); S.friction = take(n);
     S.mu = take(nc); S.gravity_z = take(1);
-    S.steps = h->steps; S.episode = h->episode; S.reset_id = h->reset_id; S.ret = h->ret;
+    S.steps = h->steps; S.episode = h->episode; S.reset_id = h->reset_id; S.ret = h->ret; S.cls = h->cls;
     S.n_envs = N; S.first_env_id = h->first_env_id; S.seed = h->seed;
 }
 
@@ -240,6 +247,7 @@ int set_state_impl(os2r_env *h, StateDev<T> &S, const double *in) {
         ap[e] = row[2 * n + h->rows];
         ap[N + e] = row[2 * n + h->rows + 1];
     }
+    CK(cudaMemset(h->cls, 0xFF, (size_t)N));   // sorting hint unknown for a state written from outside
     return put_real(h, S.q_hi, n, hi) || put_real(h, S.q_lo, n, lo) || put_real(h, S.qd, n, qd) || put_real(h, S.qd_lo, n, qdl) ||
            put_real(h, S.lam, h->rows, lam) || put_real(h, S.a_prev, 2, ap);
 }
@@ -277,10 +285,10 @@ int do_step(os2r_env *h, const float *actions, float *obs, float *reward, uint8_
             int32_t *info, cudaStream_t stream) {
     cudaError_t e;
     if (h->precision == 32)
-        e = launch_step<float>(h->model.n_dof, h->model.n_contacts, h->m32, h->taskdev, h->s32, actions, obs, reward,
+        e = launch_step<float>(h->model.n_dof, h->model.n_contacts, h->block, h->m32, h->taskdev, h->s32, actions, obs, reward,
                                done, term, info, h->stats, stream);
     else
-        e = launch_step<double>(h->model.n_dof, h->model.n_contacts, h->m64, h->taskdev, h->s64, actions, obs, reward,
+        e = launch_step<double>(h->model.n_dof, h->model.n_contacts, h->block, h->m64, h->taskdev, h->s64, actions, obs, reward,
                                 done, term, info, h->stats, stream);
     if (e != cudaSuccess) return fail("step kernel launch failed: %s", cudaGetErrorString(e));
     h->launches += 1;
@@ -306,6 +314,7 @@ int32_t os2r_create(const os2r_model *model, const os2r_task_cfg *task, int64_t 
     if (model->n_dof < 2 || model->n_dof > OS2R_MAX_DOF) return fail("os2r_create: n_dof %d unsupported (2..5)", model->n_dof);
     if (model->n_contacts != OS2R_NC) return fail("os2r_create: n_contacts %d unsupported (kernels are built for %d proxies)", model->n_contacts, OS2R_NC);
     if (precision != 32 && precision != 64) return fail("os2r_create: precision must be 32 or 64");
+    if (!(model->pgs_tol >= 0.0)) return fail("os2r_create: pgs_tol must be >= 0");
     if (task->obs_dim <= 0 || task->obs_dim > OS2R_MAX_OBS) return fail("os2r_create: obs_dim %d out of range", task->obs_dim);
     if (task->n_resets <= 0 || task->n_resets > OS2R_MAX_RESETS) return fail("os2r_create: n_resets %d out of range", task->n_resets);
     if (model->role_dof[OS2R_ROLE_HIP] < 0 || model->role_dof[OS2R_ROLE_KNEE] < 0) return fail("os2r_create: model lacks hip/knee joints");
@@ -319,8 +328,15 @@ int32_t os2r_create(const os2r_model *model, const os2r_task_cfg *task, int64_t 
                     ce == cudaSuccess ? "device count 0" : cudaGetErrorString(ce));
     if (device < 0 || device >= ndev) return fail("os2r_create: device %d out of range (0..%d)", device, ndev - 1);
     DeviceGuard guard(device);
+    int sm_count = 0;
+    if (cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || sm_count <= 0)
+        return fail("os2r_create: cannot query the SM count of device %d", device);
 
     os2r_env *h = new os2r_env();
+    h->sm_count = sm_count;
+    const char *force_block = getenv("OS2R_FORCE_BLOCK");   // experiments only
+    h->block = precision == 32 ? step_block_threads<float>(n_envs, sm_count) : step_block_threads<double>(n_envs, sm_count);
+    if (force_block && (atoi(force_block) == OS2R_BLOCK || (precision == 32 && atoi(force_block) == OS2R_BLOCK_WIDE))) h->block = atoi(force_block);
     h->model = *model; h->task = *task; h->precision = precision; h->device = device;
     h->n = n_envs; h->first_env_id = first_env_id; h->seed = seed;
     h->rows = model->n_dof + 3 * model->n_contacts;
@@ -346,6 +362,7 @@ int32_t os2r_create(const os2r_model *model, const os2r_task_cfg *task, int64_t 
     if ((e = cudaMalloc(&h->episode, n_envs * sizeof(uint32_t))) != cudaSuccess) return cleanup("cudaMalloc(episode)", e);
     if ((e = cudaMalloc(&h->reset_id, n_envs * sizeof(int32_t))) != cudaSuccess) return cleanup("cudaMalloc(reset_id)", e);
     if ((e = cudaMalloc(&h->ret, n_envs * sizeof(double))) != cudaSuccess) return cleanup("cudaMalloc(ret)", e);
+    if ((e = cudaMalloc(&h->cls, n_envs)) != cudaSuccess) return cleanup("cudaMalloc(cls)", e);
     if ((e = cudaMalloc(&h->stats, sizeof(StatsDev))) != cudaSuccess) return cleanup("cudaMalloc(stats)", e);
     if ((e = cudaMemset(h->stats, 0, sizeof(StatsDev))) != cudaSuccess) return cleanup("cudaMemset(stats)", e);
     if (precision == 32) { carve<float>(h, h->s32); e = launch_init<float>(h->taskdev, h->s32, model->gravity_z, 0); }
@@ -360,7 +377,7 @@ int32_t os2r_create(const os2r_model *model, const os2r_task_cfg *task, int64_t 
 int32_t os2r_destroy(os2r_env *h) {
     if (!h) return 0;
     DeviceGuard guard(h->device);
-    cudaFree(h->real_block); cudaFree(h->steps); cudaFree(h->episode); cudaFree(h->reset_id); cudaFree(h->ret);
+    cudaFree(h->real_block); cudaFree(h->steps); cudaFree(h->episode); cudaFree(h->reset_id); cudaFree(h->ret); cudaFree(h->cls);
     cudaFree(h->stats);
     if (h->host_io_ready || h->host_stream) {
         cudaFreeHost(h->pin_actions); cudaFreeHost(h->pin_obs); cudaFreeHost(h->pin_term); cudaFreeHost(h->pin_reward);
@@ -504,11 +521,11 @@ int32_t os2r_kernel_info(const os2r_env *h, int32_t *block_threads, int32_t *gri
     DeviceGuard guard(h->device);
     cudaFuncAttributes a;
     int resident = 0;
-    cudaError_t e = h->precision == 32 ? step_kernel_attributes<float>(h->model.n_dof, &a, &resident)
-                                       : step_kernel_attributes<double>(h->model.n_dof, &a, &resident);
+    cudaError_t e = h->precision == 32 ? step_kernel_attributes<float>(h->model.n_dof, h->block, &a, &resident)
+                                       : step_kernel_attributes<double>(h->model.n_dof, h->block, &a, &resident);
     if (e != cudaSuccess) return fail("cudaFuncGetAttributes failed: %s", cudaGetErrorString(e));
-    if (block_threads) *block_threads = OS2R_BLOCK;
-    if (grid_blocks) *grid_blocks = (int32_t)((h->n + OS2R_BLOCK - 1) / OS2R_BLOCK);
+    if (block_threads) *block_threads = h->block;
+    if (grid_blocks) *grid_blocks = (int32_t)((h->n + h->block - 1) / h->block);
     if (regs_per_thread) *regs_per_thread = a.numRegs;
     if (local_bytes_per_thread) *local_bytes_per_thread = (int32_t)a.localSizeBytes;
     if (resident_blocks_per_sm) *resident_blocks_per_sm = resident;

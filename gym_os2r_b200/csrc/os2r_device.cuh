@@ -44,6 +44,8 @@ struct ModelDev {
     T contact_pos[OS2R_MAX_CONTACTS][3];
     T contact_radius[OS2R_MAX_CONTACTS];
     T dt, erp_over_dt, max_erv, cfm_contact, cfm_joint;
+    T pgs_tol2;                  // squared energy-norm tolerance of the sweeps (os2r_model.pgs_tol)
+    T sort_margin;               // ground clearance below which a contact proxy counts as "near" (lane sorting hint)
     T max_torque[2];
     int32_t contact_body[OS2R_MAX_CONTACTS];
     int32_t hip_dof, knee_dof;
@@ -73,6 +75,8 @@ struct StateDev {
     uint32_t *episode;           // [N] episode counter (RNG counter word)
     int32_t *reset_id;           // [N]
     double *ret;                 // [N] return of the current episode
+    uint8_t *cls;                // [N] bit c: contact proxy c was near the ground after the last step. A pure
+                                 //     scheduling hint (which lanes share a warp); never changes a result.
     int64_t n_envs;
     int64_t first_env_id;
     uint64_t seed;
@@ -96,7 +100,13 @@ __device__ __forceinline__ float rsqrt_t(float x) {
     return fmaf(r, fmaf(-0.5f * x * r, r, 0.5f), r);
 }
 __device__ __forceinline__ double rsqrt_t(double x) { return 1.0 / sqrt(x); }
-__device__ __forceinline__ float rcp_t(float x) { return 1.0f / x; }
+// MUFU.RCP (~1 ulp), no IEEE fix-up / denormal slow path: only used for the row relaxation factors 1/(A(1+cfm)),
+// whose rounding moves the sweep's fixed point by cfm * ulp (the fixed point itself does not depend on the factor)
+__device__ __forceinline__ float rcp_t(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
 __device__ __forceinline__ double rcp_t(double x) { return 1.0 / x; }
 __device__ __forceinline__ float fmin_t(float a, float b) { return fminf(a, b); }
 __device__ __forceinline__ double fmin_t(double a, double b) { return fmin(a, b); }
@@ -492,12 +502,17 @@ __device__ __forceinline__ void physics_iteration(const ModelDev<T> &M, EnvRegs<
     // Row update with relative CFM c on the diagonal A(1+c):
     //   lam' = clamp(lam - (G.z - target + c*A*lam) / (A(1+c))) = clamp(lam*(1-k) - (G.z - target)*inv),
     //   1-k = 1/(1+c), inv = 1/(A(1+c)) precomputed per row.
-    // Early exit: a sweep that changes no impulse of any lane of the warp is a fixed point, so the remaining
-    // sweeps would reproduce it bit for bit — skipping them is exact (typical: saturated joint friction, no contact).
+    // Early exit (per env): the sweeps of a lane end after the first sweep whose whitened velocity change
+    // |dz| = sqrt(dv^T M dv) is <= pgs_tol (tol 0: only when the sweep left z bit-for-bit unchanged, the typical
+    // case being saturated joint friction without contact). The decision uses the lane's own data only, so a
+    // result never depends on which other envs share the warp; the warp leaves the loop when its last lane does.
     const T kj1 = T(1) / (T(1) + M.cfm_joint), kc1 = T(1) / (T(1) + M.cfm_contact);   // 1 - k
+    const T tol2 = M.pgs_tol2;
 #pragma unroll 1
     for (int it = 0; it < M.pgs_iters; ++it) {
-        T chg = 0;       // max |delta lambda| of this sweep (exactly 0 <=> fixed point)
+        T zs[N];
+#pragma unroll
+        for (int k = 0; k < N; ++k) zs[k] = z[k];
 #pragma unroll
         for (int r = 0; r < N; ++r) {
             // branch-free: a row without friction has bound 0, so its impulse stays 0 and the update adds 0
@@ -511,7 +526,6 @@ __device__ __forceinline__ void physics_iteration(const ModelDev<T> &M, EnvRegs<
 #pragma unroll
             for (int k = r; k < N; ++k) z[k] += Gj[r][k] * dl;
             C(SL::LAM + r) = nl;
-            chg = fmax_t(chg, dl < T(0) ? -dl : dl);
         }
 #pragma unroll
         for (int c = 0; c < NC; ++c) {
@@ -534,11 +548,13 @@ __device__ __forceinline__ void physics_iteration(const ModelDev<T> &M, EnvRegs<
 #pragma unroll
                     for (int k = 0; k < N; ++k) z[k] += Gc[c][d][k] * dl;
                     C(SL::LAM + r) = nl;
-                    chg = fmax_t(chg, dl < T(0) ? -dl : dl);
                 }
             }
         }
-        if (!__any_sync(__activemask(), chg != T(0))) break;
+        T e2 = 0;
+#pragma unroll
+        for (int k = 0; k < N; ++k) { const T dz = z[k] - zs[k]; e2 += dz * dz; }
+        if (e2 <= tol2) break;
     }
     // ---- v = v* + L^-T z ; q += dt v  (TwoSum-compensated (hi, lo) pairs in fp32) --------------------------
     {

@@ -31,6 +31,7 @@ __device__ __noinline__ int reset_env_global(const TaskDev &K, StateDev<T> &S, i
     S.reset_id[e] = idx;
     S.steps[e] = 0;
     S.ret[e] = 0.0;
+    S.cls[e] = 0xFF;   // sorting hint unknown after a reset: treat every proxy as near the ground
     draw_params<T>(K, S, e, gid, ep);
     if (obs_row) {
         // the observation sees the state the device will actually integrate (hi+lo rounding of q)
@@ -77,32 +78,79 @@ __global__ void __launch_bounds__(OS2R_BLOCK) init_kernel(const __grid_constant_
         gz = K.cfg.grav_mean + K.cfg.grav_std * z[0];
     }
     S.gravity_z[e] = (T)gz;
-    S.steps[e] = 0; S.episode[e] = 0; S.reset_id[e] = 0; S.ret[e] = 0.0;
+    S.steps[e] = 0; S.episode[e] = 0; S.reset_id[e] = 0; S.ret[e] = 0.0; S.cls[e] = 0xFF;
+}
+
+// ------------------------------------------------------------------------------------------------
+// lane sorting: which env of the block's window each thread steps
+// ------------------------------------------------------------------------------------------------
+// A warp pays for the union of its lanes' constraint rows (each contact proxy costs ~780 instructions per
+// physics iteration as soon as ONE lane touches the ground), so the block regroups its envs by the set of
+// proxies that were near the ground after the previous step: envs lying on the ground share a warp, hopping
+// envs share the next ones, airborne envs fill the rest and never execute contact rows. Stable counting sort
+// over 2^NC classes (+1 for slots past the end of the batch), ballot/match based, once per env step.
+// The hint only decides the thread <-> env pairing; every per-env result is independent of it.
+template <int BLOCK, int NKEYS>
+__device__ __forceinline__ int sorted_source(int key, int *scratch) {
+    constexpr int W = BLOCK / 32;
+    static_assert(NKEYS * W <= 64 && NKEYS * W <= BLOCK, "two counters per lane of warp 0");
+    int *cnt = scratch;              // [NKEYS * W] counts, then exclusive offsets; heavier classes first
+    int *perm = scratch + 64;        // [BLOCK]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid < 64) cnt[tid] = 0;
+    __syncthreads();
+    const unsigned same = __match_any_sync(0xffffffffu, key);
+    const int p = (NKEYS - 1 - key) * W + warp;
+    if (lane == __ffs(same) - 1) cnt[p] = __popc(same);
+    __syncthreads();
+    if (warp == 0) {
+        const int a = cnt[2 * lane], b = cnt[2 * lane + 1];
+        int s = a + b;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, s, o);
+            if (lane >= o) s += t;
+        }
+        cnt[2 * lane] = s - a - b;
+        cnt[2 * lane + 1] = s - b;
+    }
+    __syncthreads();
+    perm[cnt[p] + __popc(same & ((1u << lane) - 1u))] = tid;
+    __syncthreads();
+    const int src = perm[tid];
+    __syncthreads();                 // the scratch area is reused for the cold slots
+    return src;
 }
 
 // ------------------------------------------------------------------------------------------------
 // the fused step kernel: substeps x physics + observation + reward + done + auto-reset
 // ------------------------------------------------------------------------------------------------
-template <typename T, int N, int NC>
+template <typename T, int N, int NC, int BLOCK>
 #ifdef OS2R_MAXNREG
-__global__ void __maxnreg__(OS2R_MAXNREG)
+__global__ void __maxnreg__(sizeof(T) == 4 ? OS2R_MAXNREG : 255)
 #else
-__global__ void __launch_bounds__(OS2R_BLOCK, (sizeof(T) == 4 ? OS2R_MIN_BLOCKS : 1))
+__global__ void __launch_bounds__(BLOCK, (sizeof(T) == 4 ? OS2R_RESIDENT_THREADS / BLOCK : 1))
 #endif
 step_kernel(const __grid_constant__ ModelDev<T> M, const __grid_constant__ TaskDev K, StateDev<T> S,
             const float *__restrict__ actions, float *__restrict__ obs, float *__restrict__ reward,
             uint8_t *__restrict__ done, float *__restrict__ term_obs, int32_t *__restrict__ info,
             StatsDev *stats) {
+    static_assert(NC <= 3, "class byte: one bit per contact proxy, 2^NC + 1 sort keys");
     const int64_t NE = S.n_envs;
-    // Threads past the end of the batch (last block only) shadow the last env instead of exiting, so that the
-    // block-wide barriers inside the physics loop stay legal; they leave before anything is written.
-    const int64_t e_raw = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool valid = e_raw < NE;
-    const int64_t e = valid ? e_raw : NE - 1;
     using SL = ColdSlots<N, NC>;
     constexpr int ROWS = SL::ROWS;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const Cold<T, OS2R_BLOCK> C{reinterpret_cast<T *>(smem_raw) + threadIdx.x};
+    // Thread t steps env (block window start + src). Slots past the end of the batch (last block only) sort last
+    // and shadow the last env instead of exiting, so that the block-wide barriers inside the physics loop stay
+    // legal; they leave before anything is written.
+    const int64_t window = (int64_t)blockIdx.x * BLOCK;
+    const bool nominal_valid = window + threadIdx.x < NE;
+    const int key = nominal_valid ? 1 + (int)(__ldcg(S.cls + window + threadIdx.x) & ((1u << NC) - 1u)) : 0;
+    const int src = sorted_source<BLOCK, (1 << NC) + 1>(key, reinterpret_cast<int *>(smem_raw));
+    const int64_t e_raw = window + src;
+    const bool valid = e_raw < NE;
+    const int64_t e = valid ? e_raw : NE - 1;
+    const Cold<T, BLOCK> C{reinterpret_cast<T *>(smem_raw) + threadIdx.x};
 
     EnvRegs<T, N> E;
     // ---- prologue: ALL global loads are issued back to back (explicit ld.global, so the compiler may hoist
@@ -148,7 +196,10 @@ step_kernel(const __grid_constant__ ModelDev<T> M, const __grid_constant__ TaskD
 #pragma unroll
     for (int r = 0; r < ROWS; ++r) C(SL::LAM + r) = ld_lam[r];
 #pragma unroll
-    for (int c = 0; c < NC; ++c) C(SL::MU + c) = ld_mu[c];
+    for (int c = 0; c < NC; ++c) {
+        C(SL::MU + c) = ld_mu[c];
+        C(SL::CX + 3 * c + 2) = T(0);   // defined even when substeps == 0 (reads as "near")
+    }
     C(SL::AOLD) = a_old0;
     C(SL::AOLD + 1) = a_old1;
     C(SL::MISC) = __int_as_float_t<T>(steps_in);
@@ -157,10 +208,12 @@ step_kernel(const __grid_constant__ ModelDev<T> M, const __grid_constant__ TaskD
 
 #pragma unroll 1
     for (int s = 0; s < M.substeps; ++s) {
-        // Keep the block's warps in phase: all warps of an SM run the same ~45 KB loop body, and warps that drift
-        // apart thrash the 32 KB instruction cache (`no_instruction` was a top stall; measured -3..4 % step time).
+        // Keep the block's warps in phase: all warps of an SM run the same ~41 KB loop body, and warps that drift
+        // apart thrash the instruction caches (measured: -3..4 % step time with the two barriers per iteration;
+        // a rolled forward pass that fits the 32 KB cache still lost 12 % without them and 20 % overall to its
+        // extra instructions and spills — DESIGN.md section 9).
         __syncthreads();
-        physics_iteration<T, N, NC, Cold<T, OS2R_BLOCK>>(M, E, C);
+        physics_iteration<T, N, NC, Cold<T, BLOCK>>(M, E, C);
     }
     if (!valid) return;
 
@@ -200,8 +253,14 @@ step_kernel(const __grid_constant__ ModelDev<T> M, const __grid_constant__ TaskD
         atomicAdd(&stats->sum_length, (double)steps);
     }
     if (cause && (K.cfg.auto_reset || !finite)) {
-        reset_idx = reset_env_global<T, N, NC>(K, S, e, a_old, obs + e * D);
+        reset_idx = reset_env_global<T, N, NC>(K, S, e, a_old, obs + e * D);   // also marks the env "unknown" (all near)
     } else {
+        // next step's sorting hint: which proxies ended within sort_margin of the ground
+        unsigned cls = 0;
+#pragma unroll
+        for (int c = 0; c < NC; ++c)
+            if (!(C(SL::CX + 3 * c + 2) - M.contact_radius[c] >= M.sort_margin)) cls |= 1u << c;
+        S.cls[e] = (uint8_t)cls;
 #pragma unroll
         for (int i = 0; i < N; ++i) {
             S.q_hi[i * NE + e] = E.q_hi[i];
@@ -241,7 +300,7 @@ __global__ void __launch_bounds__(256) fma_peak_kernel(float *out, int iters, fl
 // ------------------------------------------------------------------------------------------------
 // launchers (dispatch on n_dof; all shipped models carry 3 contact proxies)
 // ------------------------------------------------------------------------------------------------
-static inline int grid_for(int64_t n) { return (int)((n + OS2R_BLOCK - 1) / OS2R_BLOCK); }
+static inline int grid_for(int64_t n, int block) { return (int)((n + block - 1) / block); }
 
 #define OS2R_DISPATCH_N(n_dof, CALL)                 \
     switch (n_dof) {                                 \
@@ -252,40 +311,86 @@ static inline int grid_for(int64_t n) { return (int)((n + OS2R_BLOCK - 1) / OS2R
     default: return cudaErrorInvalidValue;           \
     }
 
+template <typename T, int N, int BLOCK>
+static constexpr size_t step_smem_bytes() {
+    size_t cold = (size_t)ColdSlots<N, OS2R_NC>::COUNT * BLOCK * sizeof(T), sort = (size_t)(64 + BLOCK) * sizeof(int);
+    return cold > sort ? cold : sort;
+}
+
+// Wide blocks (7 warps) give the lane sort enough envs to fill whole warps with one class; they need at least one
+// block per SM to pay off. Small batches and the fp64 verification build keep 2-warp blocks (more SMs busy).
 template <typename T>
-cudaError_t launch_step(int n_dof, int n_contacts, const ModelDev<T> &M, const TaskDev &K, const StateDev<T> &S,
+int step_block_threads(int64_t n_envs, int sm_count) {
+    if (sizeof(T) == 4 && n_envs >= (int64_t)sm_count * OS2R_BLOCK_WIDE) return OS2R_BLOCK_WIDE;
+    return OS2R_BLOCK;
+}
+
+template <typename T, int N, int BLOCK>
+static cudaError_t launch_step_n(const ModelDev<T> &M, const TaskDev &K, const StateDev<T> &S, const float *actions, float *obs,
+                                 float *reward, uint8_t *done, float *term_obs, int32_t *info, StatsDev *stats, cudaStream_t stream) {
+    constexpr size_t smem = step_smem_bytes<T, N, BLOCK>();
+    if (smem > 48 * 1024) {
+        static bool raised = false;   // per kernel instantiation
+        if (!raised) {
+            cudaError_t e = cudaFuncSetAttribute(step_kernel<T, N, OS2R_NC, BLOCK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            raised = true;
+        }
+    }
+    step_kernel<T, N, OS2R_NC, BLOCK><<<grid_for(S.n_envs, BLOCK), BLOCK, smem, stream>>>(M, K, S, actions, obs, reward, done, term_obs, info, stats);
+    return cudaGetLastError();
+}
+
+template <typename T>
+cudaError_t launch_step(int n_dof, int n_contacts, int block, const ModelDev<T> &M, const TaskDev &K, const StateDev<T> &S,
                         const float *actions, float *obs, float *reward, uint8_t *done, float *term_obs,
                         int32_t *info, StatsDev *stats, cudaStream_t stream) {
     if (n_contacts != OS2R_NC) return cudaErrorInvalidValue;
-    OS2R_DISPATCH_N(n_dof, (step_kernel<T, N_, OS2R_NC><<<grid_for(S.n_envs), OS2R_BLOCK,
-                                                          ColdSlots<N_, OS2R_NC>::COUNT * OS2R_BLOCK * sizeof(T), stream>>>(
-                               M, K, S, actions, obs, reward, done, term_obs, info, stats)));
-    return cudaGetLastError();
+    if (sizeof(T) == 4 && block == OS2R_BLOCK_WIDE) {
+        if constexpr (sizeof(T) == 4) {
+            OS2R_DISPATCH_N(n_dof, return (launch_step_n<T, N_, OS2R_BLOCK_WIDE>(M, K, S, actions, obs, reward, done, term_obs, info, stats, stream)));
+        }
+    }
+    if (block != OS2R_BLOCK) return cudaErrorInvalidValue;
+    OS2R_DISPATCH_N(n_dof, return (launch_step_n<T, N_, OS2R_BLOCK>(M, K, S, actions, obs, reward, done, term_obs, info, stats, stream)));
+    return cudaErrorInvalidValue;
 }
 
 template <typename T>
 cudaError_t launch_reset(int n_dof, int n_contacts, const TaskDev &K, const StateDev<T> &S, const uint8_t *mask,
                          float *obs, cudaStream_t stream) {
     if (n_contacts != OS2R_NC) return cudaErrorInvalidValue;
-    OS2R_DISPATCH_N(n_dof, (reset_kernel<T, N_, OS2R_NC><<<grid_for(S.n_envs), OS2R_BLOCK, 0, stream>>>(K, S, mask, obs)));
+    OS2R_DISPATCH_N(n_dof, (reset_kernel<T, N_, OS2R_NC><<<grid_for(S.n_envs, OS2R_BLOCK), OS2R_BLOCK, 0, stream>>>(K, S, mask, obs)));
     return cudaGetLastError();
 }
 
 template <typename T>
 cudaError_t launch_init(const TaskDev &K, const StateDev<T> &S, double nominal_gz, cudaStream_t stream) {
-    init_kernel<T><<<grid_for(S.n_envs), OS2R_BLOCK, 0, stream>>>(K, S, nominal_gz);
+    init_kernel<T><<<grid_for(S.n_envs, OS2R_BLOCK), OS2R_BLOCK, 0, stream>>>(K, S, nominal_gz);
     return cudaGetLastError();
 }
 
-template <typename T>
-cudaError_t step_kernel_attributes(int n_dof, cudaFuncAttributes *attr, int *blocks_per_sm) {
-    OS2R_DISPATCH_N(n_dof, {
-        cudaError_t e = cudaFuncGetAttributes(attr, step_kernel<T, N_, OS2R_NC>);
+template <typename T, int N, int BLOCK>
+static cudaError_t step_attr_n(cudaFuncAttributes *attr, int *blocks_per_sm) {
+    constexpr size_t smem = step_smem_bytes<T, N, BLOCK>();
+    cudaError_t e = cudaFuncGetAttributes(attr, step_kernel<T, N, OS2R_NC, BLOCK>);
+    if (e != cudaSuccess) return e;
+    if (smem > 48 * 1024) {
+        e = cudaFuncSetAttribute(step_kernel<T, N, OS2R_NC, BLOCK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, step_kernel<T, N_, OS2R_NC>, OS2R_BLOCK,
-                                                             ColdSlots<N_, OS2R_NC>::COUNT * OS2R_BLOCK * sizeof(T));
-    });
-    return cudaSuccess;
+    }
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, step_kernel<T, N, OS2R_NC, BLOCK>, BLOCK, smem);
+}
+
+template <typename T>
+cudaError_t step_kernel_attributes(int n_dof, int block, cudaFuncAttributes *attr, int *blocks_per_sm) {
+    if (sizeof(T) == 4 && block == OS2R_BLOCK_WIDE) {
+        if constexpr (sizeof(T) == 4) {
+            OS2R_DISPATCH_N(n_dof, return (step_attr_n<T, N_, OS2R_BLOCK_WIDE>(attr, blocks_per_sm)));
+        }
+    }
+    OS2R_DISPATCH_N(n_dof, return (step_attr_n<T, N_, OS2R_BLOCK>(attr, blocks_per_sm)));
+    return cudaErrorInvalidValue;
 }
 
 cudaError_t launch_fma_peak(float *out, int blocks, int iters, cudaStream_t stream) {
@@ -294,13 +399,14 @@ cudaError_t launch_fma_peak(float *out, int blocks, int iters, cudaStream_t stre
 }
 
 #define OS2R_INSTANTIATE(T)                                                                                   \
-    template cudaError_t launch_step<T>(int, int, const ModelDev<T> &, const TaskDev &, const StateDev<T> &,  \
+    template int step_block_threads<T>(int64_t, int);                                                         \
+    template cudaError_t launch_step<T>(int, int, int, const ModelDev<T> &, const TaskDev &, const StateDev<T> &, \
                                         const float *, float *, float *, uint8_t *, float *, int32_t *,       \
                                         StatsDev *, cudaStream_t);                                            \
     template cudaError_t launch_reset<T>(int, int, const TaskDev &, const StateDev<T> &, const uint8_t *,     \
                                          float *, cudaStream_t);                                              \
     template cudaError_t launch_init<T>(const TaskDev &, const StateDev<T> &, double, cudaStream_t);          \
-    template cudaError_t step_kernel_attributes<T>(int, cudaFuncAttributes *, int *);
+    template cudaError_t step_kernel_attributes<T>(int, int, cudaFuncAttributes *, int *);
 OS2R_INSTANTIATE(float)
 OS2R_INSTANTIATE(double)
 

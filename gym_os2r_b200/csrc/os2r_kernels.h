@@ -2,21 +2,25 @@
 #pragma once
 #include "os2r_device.cuh"
 
-// Launch geometry of the step kernel. 64-thread blocks: 65 536 envs -> 1024 blocks over 148 SMs =
-// 6.92 blocks/SM, so with >= 7 resident blocks/SM the whole batch is ONE balanced wave
-// (7 x 64 = 448 threads/SM => at most 65536/448 = 146 -> 144 registers per thread).
+// Launch geometry of the step kernel. The fp32 kernel is compiled for 448 resident threads per SM (65 536 envs over
+// 148 SMs = 443 threads/SM: ONE balanced wave; 65536/448 -> at most 144 registers per thread), either as 7 blocks of
+// 2 warps (small batches: more SMs busy) or as 2 blocks of 7 warps (large batches: the lane sort of os2r_kernels.cu
+// needs a few hundred envs per block to fill whole warps with one contact class).
 #ifndef OS2R_BLOCK
 #define OS2R_BLOCK 64
 #endif
-#ifndef OS2R_MIN_BLOCKS
-#define OS2R_MIN_BLOCKS 7
+#ifndef OS2R_BLOCK_WIDE
+#define OS2R_BLOCK_WIDE 224
 #endif
+#define OS2R_RESIDENT_THREADS 448
 #define OS2R_NC 3
 
 namespace os2r {
 
 template <typename T>
-cudaError_t launch_step(int n_dof, int n_contacts, const ModelDev<T> &M, const TaskDev &K, const StateDev<T> &S,
+int step_block_threads(int64_t n_envs, int sm_count);
+template <typename T>
+cudaError_t launch_step(int n_dof, int n_contacts, int block, const ModelDev<T> &M, const TaskDev &K, const StateDev<T> &S,
                         const float *actions, float *obs, float *reward, uint8_t *done, float *term_obs,
                         int32_t *info, StatsDev *stats, cudaStream_t stream);
 template <typename T>
@@ -25,7 +29,7 @@ cudaError_t launch_reset(int n_dof, int n_contacts, const TaskDev &K, const Stat
 template <typename T>
 cudaError_t launch_init(const TaskDev &K, const StateDev<T> &S, double nominal_gz, cudaStream_t stream);
 template <typename T>
-cudaError_t step_kernel_attributes(int n_dof, cudaFuncAttributes *attr, int *blocks_per_sm);
+cudaError_t step_kernel_attributes(int n_dof, int block, cudaFuncAttributes *attr, int *blocks_per_sm);
 cudaError_t launch_fma_peak(float *out, int blocks, int iters, cudaStream_t stream);
 
 }  // namespace os2r

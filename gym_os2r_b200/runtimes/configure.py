@@ -9,7 +9,7 @@ from ..tasks.monopod import build_task_cfg
 def configure(task_cls, agent_rate: float = 1000, physics_rate: float = 10000, *,
               max_episode_steps: int = 0, auto_reset: bool = False, reset_randomized: bool = False,
               randomize_params: bool = False, randomize_gravity: bool = False, randomization: dict = None,
-              pgs_iters: int = None, substeps: int = None, **task_kwargs) -> Tuple[object, compiler.CompiledModel, _capi.TaskCfg]:
+              pgs_iters: int = None, pgs_tol: float = None, substeps: int = None, **task_kwargs) -> Tuple[object, compiler.CompiledModel, _capi.TaskCfg]:
     """Create the task, its spaces, the compiled model tables and the device task configuration."""
     task = task_cls(agent_rate=agent_rate, **task_kwargs)
     task.create_spaces()
@@ -18,6 +18,8 @@ def configure(task_cls, agent_rate: float = 1000, physics_rate: float = 10000, *
     physics['dt'] = 1.0 / physics_rate
     if pgs_iters is not None:
         physics['pgs_iters'] = int(pgs_iters)
+    if pgs_tol is not None:
+        physics['pgs_tol'] = float(pgs_tol)
     model_name = task.cfg.get_config(f'task_modes/{task.task_mode}/model')
     compiled = compiler.compile_model(model_name, physics, max_torque=tuple(task.max_torques))
     cfg = build_task_cfg(task, compiled, max_episode_steps=max_episode_steps, auto_reset=auto_reset,

@@ -35,7 +35,8 @@ class CudaRuntime(Env):
     def __init__(self, task_cls: type, agent_rate: float, physics_rate: float, real_time_factor: float = None,
                  physics_engine=None, world: str = None, num_envs: int = 1, device: int = 0,
                  seed: Optional[int] = None, max_episode_steps: int = 0, auto_reset: Optional[bool] = None,
-                 precision: int = 32, first_env_id: int = 0, pgs_iters: Optional[int] = None, **kwargs):
+                 precision: int = 32, first_env_id: int = 0, pgs_iters: Optional[int] = None, pgs_tol: Optional[float] = None,
+                 **kwargs):
         steps = physics_rate / agent_rate
         if steps != int(steps):
             warnings.warn(f'Rounding the number of iterations to {int(steps)} from the nominal {steps}')
@@ -51,7 +52,7 @@ class CudaRuntime(Env):
         self._opts = dict(max_episode_steps=int(max_episode_steps or 0),
                           auto_reset=self.batched if auto_reset is None else bool(auto_reset),
                           reset_randomized=False, randomize_params=False, randomize_gravity=False,
-                          randomization=None, pgs_iters=pgs_iters)
+                          randomization=None, pgs_iters=pgs_iters, pgs_tol=pgs_tol)
         self._engine: Optional[Engine] = None
         self._build_task()
         self._gazebo = SimulatorShim(self)

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define OS2R_ABI_VERSION 4
+#define OS2R_ABI_VERSION 5
 
 #define OS2R_MAX_DOF 5
 #define OS2R_MAX_CONTACTS 4
@@ -90,6 +90,9 @@ typedef struct os2r_model {
     double erp, max_erv;              /* contact error reduction: min(depth*erp/dt, max_erv)     */
     double cfm_contact, cfm_joint;    /* relative constraint force mixing on the diagonal        */
     double max_torque[2];             /* hip, knee (settings.yaml:13-14)                         */
+    double pgs_tol;                   /* > 0: an env's sweeps end after the first sweep whose velocity
+                                         change sqrt(dv^T M dv) is <= pgs_tol (kinetic-energy norm,
+                                         sqrt(kg) m/s); pgs_iters is then the cap. 0: always pgs_iters  */
 } os2r_model;
 
 /* Task / reward / termination / reset configuration (replaces MonopodTask.create_spaces,

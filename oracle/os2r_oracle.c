@@ -300,11 +300,38 @@ static void build_constraints(const os2r_model *M, const env_params *P, const do
     }
 }
 
+/* Diagnostic: how many sweeps each physics iteration ran (index = sweeps, last bin = overflow). */
+static long long g_sweep_hist[65];
+void oracle_sweep_histogram(long long out[65], int clear) {
+    for (int i = 0; i < 65; ++i) { out[i] = __atomic_load_n(&g_sweep_hist[i], __ATOMIC_RELAXED); if (clear) __atomic_store_n(&g_sweep_hist[i], 0, __ATOMIC_RELAXED); }
+}
+
+/* M = Minv^-1 by Gauss-Jordan (n <= 5, SPD): only the convergence measure needs it. */
+static void invert_spd(int n, double A[NMAX][NMAX], double B[NMAX][NMAX]) {
+    double W[NMAX][2 * NMAX];
+    for (int i = 0; i < n; ++i) for (int j = 0; j < n; ++j) { W[i][j] = A[i][j]; W[i][n + j] = i == j; }
+    for (int c = 0; c < n; ++c) {
+        int p = c;
+        for (int r = c + 1; r < n; ++r) if (fabs(W[r][c]) > fabs(W[p][c])) p = r;
+        if (p != c) for (int j = 0; j < 2 * n; ++j) { double t = W[c][j]; W[c][j] = W[p][j]; W[p][j] = t; }
+        double d = 1.0 / W[c][c];
+        for (int j = 0; j < 2 * n; ++j) W[c][j] *= d;
+        for (int r = 0; r < n; ++r) if (r != c) { double f = W[r][c]; for (int j = 0; j < 2 * n; ++j) W[r][j] -= f * W[c][j]; }
+    }
+    for (int i = 0; i < n; ++i) for (int j = 0; j < n; ++j) B[i][j] = W[i][n + j];
+}
+
+/* Projected Gauss-Seidel, fixed row order, at most `sweeps` sweeps. With tol > 0 the iteration of this
+ * env ends after the first sweep whose velocity change is <= tol in the kinetic-energy norm
+ * sqrt(dv^T M dv) (the kernel measures the same quantity as |dz| in its Cholesky-whitened coordinates). */
 static void pgs_sweeps(const os2r_model *M, const env_params *P, const constraint_set *S,
-                       double *v, double *lam, int sweeps, double tol) {
-    int n = M->n_dof, nc = M->n_contacts;
-    for (int it = 0; it < sweeps; ++it) {
-        double change = 0;
+                       double Minv[NMAX][NMAX], double *v, double *lam, int sweeps, double tol) {
+    int n = M->n_dof, it;
+    double Mass[NMAX][NMAX];
+    if (tol > 0) invert_spd(n, Minv, Mass);
+    for (it = 0; it < sweeps; ) {
+        double v0[NMAX];
+        for (int i = 0; i < n; ++i) v0[i] = v[i];
         for (int r = 0; r < S->n_rows; ++r) {
             if (!S->active[r]) continue;
             double lo, hi;
@@ -322,11 +349,15 @@ static void pgs_sweeps(const os2r_model *M, const env_params *P, const constrain
             double dl = nl - lam[r];
             for (int i = 0; i < n; ++i) v[i] += S->MiJt[r][i] * dl;
             lam[r] = nl;
-            if (fabs(dl) > change) change = fabs(dl);
         }
-        (void)nc;
-        if (tol > 0 && change < tol) break;
+        ++it;
+        if (tol > 0) {
+            double e2 = 0;
+            for (int i = 0; i < n; ++i) for (int j = 0; j < n; ++j) e2 += (v[i] - v0[i]) * Mass[i][j] * (v[j] - v0[j]);
+            if (e2 <= tol * tol) break;
+        }
     }
+    __atomic_fetch_add(&g_sweep_hist[it < 64 ? it : 64], 1, __ATOMIC_RELAXED);
 }
 
 /* One physics iteration (dt). state: q, v, lam (warm start) updated in place. */
@@ -345,7 +376,7 @@ static void substep(const os2r_model *M, const env_params *P, double *q, double 
         if (!S.active[r]) { lam[r] = 0.0; continue; }
         for (int i = 0; i < n; ++i) v[i] += S.MiJt[r][i] * lam[r];   /* warm start */
     }
-    pgs_sweeps(M, P, &S, v, lam, sweeps, tol);
+    pgs_sweeps(M, P, &S, Minv, v, lam, sweeps, tol);
     for (int i = 0; i < n; ++i) q[i] += M->dt * v[i];
 }
 
@@ -594,7 +625,7 @@ static void *step_range(void *arg) {
         double *srow = J->state + e * W, *q = srow, *v = srow + n, *lam = srow + 2*n, *a_prev = srow + 2*n + rows;
         env_params P; unpack_params(M, J->params + e * PW, &P);
         double a[2] = {J->actions[2*e], J->actions[2*e + 1]}, a_old[2] = {a_prev[0], a_prev[1]};
-        for (int s = 0; s < M->substeps; ++s) substep(M, &P, q, v, lam, a, M->pgs_iters, 0.0);
+        for (int s = 0; s < M->substeps; ++s) substep(M, &P, q, v, lam, a, M->pgs_iters, M->pgs_tol);
         double raw[OS2R_MAX_OBS], o[OS2R_MAX_OBS];
         observe(M, T, q, v, a_old, raw, o);
         double r = reward_fn(T, o, a, a_old);

@@ -9,6 +9,10 @@ from gym_os2r_b200.tasks import monopod, monopod_no_norm
 
 
 def make_config(task_mode='fixed_hip', variant='norm', reward='BalancingV1', reset_positions=('stand',), **opts):
+    """Task + compiled model + device task config. Unless a test asks otherwise the sweeps run in the exact mode
+    (pgs_tol = 0: a fixed sweep count, early exit only at a bit-exact fixed point) so that the fp64 kernel and the
+    oracle can be compared to 1e-11; the production default (settings.yaml physics/pgs_tol) is covered separately."""
+    opts.setdefault('pgs_tol', 0.0)
     cls = monopod.MonopodTask if variant == 'norm' else monopod_no_norm.MonopodTask
     with warnings.catch_warnings():
         warnings.simplefilter('ignore')

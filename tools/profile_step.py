@@ -16,8 +16,7 @@ envs.output = 'torch'
 envs.reset()
 eng = envs.runtime.engine
 g = torch.Generator(device='cuda'); g.manual_seed(0)
-acts = [torch.rand((N, 2), device='cuda', generator=g) * 2 - 1 for _ in range(4)]
 for i in range(steps):
-    eng.step(acts[i % 4])
+    eng.step(torch.rand((N, 2), device='cuda', generator=g) * 2 - 1)   # fresh actions: a short cycle biases every env
 torch.cuda.synchronize()
 print('ok', eng.kernel_launches, eng.kernel_info())
