@@ -253,7 +253,8 @@ def main():
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_s = float(te[0])
     D = eng.obs_dim
-    h2d, d2h = N * 2 * 4, N * (D * 4 + 4 + 1 + 8)      # actions in; obs + reward + done + info[2] out
+    # actions in; out = ONE packed block: obs + reward + done + reset-id byte per env + the terminal-record prefix
+    h2d, d2h = N * 2 * 4, int(next(iter(eng._packed_layouts.values())).total_bytes)
 
     # the path's only collective: reduce episode statistics over ranks (NCCL over NVLink)
     st = eng.stats()
@@ -276,12 +277,12 @@ def main():
             pass
         hbm_peak = peaks.get('hbm_gbs', 6650.0)
         # DRAM traffic per launch of the step kernel from the committed `ncu --set full` capture of this workload
-        # (profiles/r1_step_kernel_final_steady.txt: dram__bytes_read.sum + dram__bytes_write.sum), else null.
+        # (profiles/r1_step_kernel_steady.txt: dram__bytes_read.sum + dram__bytes_write.sum), else null.
         traffic = None
         try:
             tot = 0.0
             unit_scale = {'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}
-            for ln in open(os.path.join(ROOT, 'profiles', 'r1_step_kernel_final_steady.txt')):
+            for ln in open(os.path.join(ROOT, 'profiles', 'r1_step_kernel_steady.txt')):
                 if ln.startswith('dram__bytes_read.sum') or ln.startswith('dram__bytes_write.sum'):
                     _, val, unit = ln.split()
                     tot += float(val) * unit_scale[unit]
@@ -290,19 +291,19 @@ def main():
             pass
         line = dict(base, value=value, ms_per_step=total_ms / K, dtype='f32',
                     config={'workload': workload, 'envs_per_gpu': N, 'n_dof': N_DOF, 'obs_dim': OBS_DIM,
-                            'pgs_iters': int(rt._compiled.struct.pgs_iters),
+                            'pgs_iters': int(rt._compiled.struct.pgs_iters), 'pgs_tol': float(rt._compiled.struct.pgs_tol),
                             'l2': 'flushed between timed steps (256 MiB memset outside each per-step CUDA-event pair); '
                                   'per-env state (26 MB) is otherwise L2-resident',
                             'hot_l2_value': world * N * K / (hot_ms * 1e-3), 'hot_l2_ms_per_step': hot_ms / K,
                             'wall_s_timed_region_incl_flush': wall, 'parallelism': f'env-sharded x{world}, no data-path collective'},
                     clocks=sampler.result(),
                     e2e={'value': world * N * K2 / e2e_s, 'unit': 'env-steps/s', 'h2d_bytes_per_step': h2d,
-                         'd2h_bytes_per_step': d2h, 'steps': K2, 'api': 'make_mp_envs(...).step(numpy) -> os2r_step_host'},
+                         'd2h_bytes_per_step': d2h, 'steps': K2, 'api': 'make_mp_envs(...).step(numpy) -> os2r_step_host_packed (pageable numpy in, one pinned block out)'},
                     gpu_launches=int(launches),
                     roofline={'bound': 'fp32', 'achieved': achieved_tf, 'peak': fp32_peak, 'unit': 'TFLOP/s',
                               'frac': achieved_tf / fp32_peak if fp32_peak else None, 'traffic': traffic,
                               'traffic_note': 'bytes per launch, ncu capture in profiles/ (algorithmic: %d)' % (N * B),
-                              'kernel': f'step_kernel<float,{N_DOF},3>', 'flop_per_env_step': F,
+                              'kernel': f'step_kernel<float,{N_DOF},3,{kinfo["block_threads"]}>', 'flop_per_env_step': F,
                               'peak_source': 'FFMA microbenchmark measured in this run (os2r_measure_fp32_peak); '
                                              'MEASURED_PEAKS.json has no fp32 entry',
                               'hbm': {'achieved': N * B / kern_s / 1e9, 'peak': hbm_peak, 'unit': 'GB/s',

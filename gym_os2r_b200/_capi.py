@@ -13,7 +13,7 @@ MAX_OBS = 12
 MAX_RESETS = 8
 MAX_ROWS = MAX_DOF + 3 * MAX_CONTACTS
 N_ROLES = 5
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 ROLE_HIP, ROLE_KNEE, ROLE_PITCH, ROLE_YAW, ROLE_BOOM_CONNECTOR = range(5)
 ROLE_OF_JOINT = {
@@ -70,6 +70,15 @@ class TaskCfg(C.Structure):
     ]
 
 
+class PackedLayout(C.Structure):
+    """struct os2r_packed_layout"""
+    _fields_ = [
+        ('obs', C.c_int64), ('reward', C.c_int64), ('done', C.c_int64), ('reset_id', C.c_int64),
+        ('term_count', C.c_int64), ('term_records', C.c_int64), ('total_bytes', C.c_int64),
+        ('record_words', _i32), ('prefix_records', _i32),
+    ]
+
+
 class Stats(C.Structure):
     """struct os2r_stats"""
     _fields_ = [
@@ -101,6 +110,9 @@ SYMBOLS = {
     'os2r_reset': (_i32, [_vp, _vp, _vp, _vp]),
     'os2r_step': (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     'os2r_step_host': (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    'os2r_packed_layout_get': (_i32, [_vp, _i32, C.POINTER(PackedLayout)]),
+    'os2r_step_host_packed': (_i32, [_vp, _vp, _vp, _i32, C.POINTER(_i32)]),
+    'os2r_fetch_terminal_records': (_i32, [_vp, _i32, _i32, _vp]),
     'os2r_get_state': (_i32, [_vp, _vp]),
     'os2r_set_state': (_i32, [_vp, _vp]),
     'os2r_get_params': (_i32, [_vp, _vp]),

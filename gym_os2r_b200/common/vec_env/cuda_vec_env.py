@@ -16,10 +16,22 @@ import torch
 
 class LazyInfos(Sequence):
     """The per-env ``info`` dicts of a step, built on access: materialising 65 536 dicts per step
-    would cost more than the physics. ``infos[i]`` / iteration / ``len`` behave like the reference's tuple."""
+    would cost more than the physics. ``infos[i]`` / iteration / ``len`` behave like the reference's tuple.
 
-    def __init__(self, names, reset_ids, done, terminal_obs, cause):
-        self._names, self._rid, self._done, self._term, self._cause = names, reset_ids, done, terminal_obs, cause
+    The terminal observations are held sparsely — one row per env that finished an episode in this step
+    (``terminal_indices`` / ``terminal_observations`` give them in bulk; ``infos[i]['terminal_observation']`` looks
+    the row up) — because a dense [N, D] copy of them would double the device-to-host traffic of a step."""
+
+    def __init__(self, names, reset_ids, done, term_idx, term_cause, term_obs):
+        self._names, self._rid, self._done = names, reset_ids, done
+        self.terminal_indices, self.terminal_causes, self.terminal_observations = term_idx, term_cause, term_obs
+        self._row_of = None
+
+    @classmethod
+    def from_dense(cls, names, reset_ids, done, terminal_obs, cause):
+        idx = np.flatnonzero(done)
+        rows = terminal_obs[idx] if terminal_obs is not None else None
+        return cls(names, reset_ids, done, idx, np.asarray(cause)[idx], rows)
 
     def __len__(self):
         return len(self._rid)
@@ -31,9 +43,12 @@ class LazyInfos(Sequence):
             i += len(self)
         d = {'reset_orientation': self._names[int(self._rid[i])]}
         if self._done[i]:
-            if self._term is not None:
-                d['terminal_observation'] = self._term[i]
-            if (int(self._cause[i]) & 3) == 2:       # ended by the TimeLimit only (gym: truncated = not done-by-task)
+            if self._row_of is None:
+                self._row_of = {int(e): k for k, e in enumerate(self.terminal_indices)}
+            k = self._row_of[int(i)]
+            if self.terminal_observations is not None:
+                d['terminal_observation'] = self.terminal_observations[k]
+            if (int(self.terminal_causes[k]) & 3) == 2:   # ended by the TimeLimit only (gym: truncated = not done-by-task)
                 d['TimeLimit.truncated'] = True
         return d
 
@@ -73,9 +88,9 @@ class CudaVecEnv:
         self._pending, self.waiting = None, False
         names = self.runtime.task.reset_positions
         if kind == 'host':
-            # numpy in / numpy out through the C-ABI host entry point (pinned staging, H2D + kernel + D2H)
-            obs, rew, done, term, info = self.runtime.engine.step_host(payload, want_terminal_obs=True, want_info=True)
-            return obs, rew, done, LazyInfos(names, info[:, 0], done, term, info[:, 1])
+            # numpy in / numpy out through the C-ABI host entry point: H2D, kernel, ONE D2H into a pinned block
+            obs, rew, done, rid, t_idx, t_cause, t_obs = self.runtime.engine.step_host_packed(payload)
+            return obs, rew, done, LazyInfos(names, rid, done, t_idx, t_cause, t_obs)
         obs, rew, done, info = payload
         if self.output == 'torch':
             return obs, rew, done, info
@@ -84,7 +99,7 @@ class CudaVecEnv:
         rid = info['reset_orientation'].cpu().numpy()
         term = info['terminal_observation'].cpu().numpy() if done_h.any() else None
         cause = info['cause'].cpu().numpy()
-        return obs.cpu().numpy(), rew.cpu().numpy(), done_h, LazyInfos(names, rid, done_h, term, cause)
+        return obs.cpu().numpy(), rew.cpu().numpy(), done_h, LazyInfos.from_dense(names, rid, done_h, term, cause)
 
     def step(self, actions):
         self.step_async(actions)

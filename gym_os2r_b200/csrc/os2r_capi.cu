@@ -147,6 +147,9 @@ struct os2r_env {
     uint8_t *dev_done = nullptr;
     int32_t *dev_info = nullptr;
     bool host_io_ready = false;
+    // single-block I/O of os2r_step_host_packed
+    unsigned char *dev_block = nullptr, *pin_block = nullptr;
+    size_t pin_block_bytes = 0;
     int64_t launches = 0;
     uint64_t env_steps = 0;
 };
@@ -281,15 +284,12 @@ int set_params_impl(os2r_env *h, StateDev<T> &S, const double *in) {
            put_real(h, S.mu, nc, mu) || put_real(h, S.gravity_z, 1, gz);
 }
 
-int do_step(os2r_env *h, const float *actions, float *obs, float *reward, uint8_t *done, float *term,
-            int32_t *info, cudaStream_t stream) {
+int do_step(os2r_env *h, const StepIO &io, cudaStream_t stream) {
     cudaError_t e;
     if (h->precision == 32)
-        e = launch_step<float>(h->model.n_dof, h->model.n_contacts, h->block, h->m32, h->taskdev, h->s32, actions, obs, reward,
-                               done, term, info, h->stats, stream);
+        e = launch_step<float>(h->model.n_dof, h->model.n_contacts, h->block, h->m32, h->taskdev, h->s32, io, h->stats, stream);
     else
-        e = launch_step<double>(h->model.n_dof, h->model.n_contacts, h->block, h->m64, h->taskdev, h->s64, actions, obs, reward,
-                                done, term, info, h->stats, stream);
+        e = launch_step<double>(h->model.n_dof, h->model.n_contacts, h->block, h->m64, h->taskdev, h->s64, io, h->stats, stream);
     if (e != cudaSuccess) return fail("step kernel launch failed: %s", cudaGetErrorString(e));
     h->launches += 1;
     h->env_steps += (uint64_t)h->n;
@@ -384,6 +384,7 @@ int32_t os2r_destroy(os2r_env *h) {
         cudaFreeHost(h->pin_done); cudaFreeHost(h->pin_info);
         cudaFree(h->dev_actions); cudaFree(h->dev_obs); cudaFree(h->dev_term); cudaFree(h->dev_reward);
         cudaFree(h->dev_done); cudaFree(h->dev_info);
+        cudaFree(h->dev_block); cudaFreeHost(h->pin_block);
         if (h->host_stream) cudaStreamDestroy(h->host_stream);
     }
     delete h;
@@ -412,7 +413,10 @@ int32_t os2r_step(os2r_env *h, const float *actions_dev, float *obs_dev, float *
     if (!h) return fail("os2r_step: null handle");
     if (!actions_dev || !obs_dev || !reward_dev || !done_dev) return fail("os2r_step: actions/obs/reward/done must be non-null");
     DeviceGuard guard(h->device);
-    return do_step(h, actions_dev, obs_dev, reward_dev, done_dev, terminal_obs_dev, info_dev, (cudaStream_t)stream);
+    StepIO io{};
+    io.actions = actions_dev; io.obs = obs_dev; io.reward = reward_dev; io.done = done_dev;
+    io.term_obs = terminal_obs_dev; io.info = info_dev;
+    return do_step(h, io, (cudaStream_t)stream);
 }
 
 // true when `p` is page-locked host memory the GPU can DMA to/from directly (cudaHostAlloc / cudaHostRegister)
@@ -437,8 +441,10 @@ int32_t os2r_step_host(os2r_env *h, const float *actions, float *obs, float *rew
     const bool pt = terminal_obs && is_pinned(terminal_obs), pi = info && is_pinned(info);
     if (!pa) memcpy(h->pin_actions, actions, N * 2 * sizeof(float));
     CK(cudaMemcpyAsync(h->dev_actions, pa ? actions : h->pin_actions, N * 2 * sizeof(float), cudaMemcpyHostToDevice, st));
-    if (do_step(h, h->dev_actions, h->dev_obs, h->dev_reward, h->dev_done, terminal_obs ? h->dev_term : nullptr,
-                info ? h->dev_info : nullptr, st)) return 1;
+    StepIO io{};
+    io.actions = h->dev_actions; io.obs = h->dev_obs; io.reward = h->dev_reward; io.done = h->dev_done;
+    io.term_obs = terminal_obs ? h->dev_term : nullptr; io.info = info ? h->dev_info : nullptr;
+    if (do_step(h, io, st)) return 1;
     CK(cudaMemcpyAsync(po ? obs : h->pin_obs, h->dev_obs, N * D * sizeof(float), cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(pr ? reward : h->pin_reward, h->dev_reward, N * sizeof(float), cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(pd ? done : h->pin_done, h->dev_done, N, cudaMemcpyDeviceToHost, st));
@@ -461,6 +467,81 @@ int32_t os2r_step_host(os2r_env *h, const float *actions, float *obs, float *rew
             memcpy(terminal_obs, obs, N * D * sizeof(float));
         }
     }
+    return 0;
+}
+
+static void packed_layout(const os2r_env *h, int32_t prefix_records, os2r_packed_layout *L) {
+    const int64_t N = h->n;
+    const int D = h->task.obs_dim;
+    auto align16 = [](int64_t x) { return (x + 15) & ~(int64_t)15; };
+    L->obs = 0;
+    L->reward = align16(L->obs + N * D * 4);
+    L->done = align16(L->reward + N * 4);
+    L->reset_id = align16(L->done + N);
+    L->term_count = align16(L->reset_id + N);
+    L->term_records = L->term_count + 16;
+    L->record_words = D + 2;
+    L->prefix_records = prefix_records;
+    L->total_bytes = L->term_records + (int64_t)prefix_records * L->record_words * 4;
+}
+
+int32_t os2r_packed_layout_get(const os2r_env *h, int32_t prefix_records, os2r_packed_layout *out) {
+    if (!h || !out) return fail("os2r_packed_layout_get: null argument");
+    if (prefix_records < 0 || prefix_records > h->n) return fail("os2r_packed_layout_get: prefix_records must be in [0, n_envs]");
+    packed_layout(h, prefix_records, out);
+    return 0;
+}
+
+int32_t os2r_step_host_packed(os2r_env *h, const float *actions, void *block, int32_t prefix_records, int32_t *n_terminal) {
+    if (!h || !actions || !block) return fail("os2r_step_host_packed: null argument");
+    if (prefix_records < 0 || prefix_records > h->n) return fail("os2r_step_host_packed: prefix_records must be in [0, n_envs]");
+    DeviceGuard guard(h->device);
+    if (ensure_host_io(h)) return 1;
+    const int64_t N = h->n;
+    os2r_packed_layout L, Lfull;
+    packed_layout(h, prefix_records, &L);
+    packed_layout(h, (int32_t)N, &Lfull);        // the device block can hold a record for every env
+    if (!h->dev_block) CK(cudaMalloc(&h->dev_block, (size_t)Lfull.total_bytes));
+    cudaStream_t st = h->host_stream;
+    const bool pa = is_pinned(actions), pb = is_pinned(block);
+    if (!pb && h->pin_block_bytes < (size_t)L.total_bytes) {
+        if (h->pin_block) cudaFreeHost(h->pin_block);
+        h->pin_block = nullptr; h->pin_block_bytes = 0;
+        CK(cudaMallocHost(&h->pin_block, (size_t)L.total_bytes));
+        h->pin_block_bytes = (size_t)L.total_bytes;
+    }
+    if (!pa) memcpy(h->pin_actions, actions, N * 2 * sizeof(float));
+    CK(cudaMemcpyAsync(h->dev_actions, pa ? actions : h->pin_actions, N * 2 * sizeof(float), cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(h->dev_block + L.term_count, 0, 16, st));
+    StepIO io{};
+    io.actions = h->dev_actions;
+    io.obs = (float *)(h->dev_block + L.obs);
+    io.reward = (float *)(h->dev_block + L.reward);
+    io.done = h->dev_block + L.done;
+    io.reset_id8 = h->dev_block + L.reset_id;
+    io.term_count = (int32_t *)(h->dev_block + L.term_count);
+    io.term_records = (int32_t *)(h->dev_block + L.term_records);
+    io.term_cap = (int32_t)N;
+    if (do_step(h, io, st)) return 1;
+    unsigned char *dst = pb ? (unsigned char *)block : h->pin_block;
+    CK(cudaMemcpyAsync(dst, h->dev_block, (size_t)L.total_bytes, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (!pb) memcpy(block, h->pin_block, (size_t)L.total_bytes);
+    if (n_terminal) *n_terminal = *(const int32_t *)((const unsigned char *)block + L.term_count);
+    return 0;
+}
+
+int32_t os2r_fetch_terminal_records(os2r_env *h, int32_t first, int32_t count, int32_t *records_host) {
+    if (!h || !records_host) return fail("os2r_fetch_terminal_records: null argument");
+    if (!h->dev_block) return fail("os2r_fetch_terminal_records: no packed step has run yet");
+    if (first < 0 || count < 0 || (int64_t)first + count > h->n) return fail("os2r_fetch_terminal_records: range out of bounds");
+    DeviceGuard guard(h->device);
+    os2r_packed_layout L;
+    packed_layout(h, 0, &L);
+    const size_t rec = (size_t)L.record_words * 4;
+    CK(cudaMemcpyAsync(records_host, h->dev_block + L.term_records + (size_t)first * rec, (size_t)count * rec,
+                       cudaMemcpyDeviceToHost, h->host_stream));
+    CK(cudaStreamSynchronize(h->host_stream));
     return 0;
 }
 

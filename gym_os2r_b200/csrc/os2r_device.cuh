@@ -82,6 +82,22 @@ struct StateDev {
     uint64_t seed;
 };
 
+// I/O buffers of one step launch. actions/obs/reward/done are mandatory; the rest is optional (null = not wanted).
+struct StepIO {
+    const float *actions;        // [N,2]
+    float *obs;                  // [N,D]
+    float *reward;               // [N]
+    uint8_t *done;               // [N] 0/1
+    float *term_obs;             // [N,D] dense terminal observation (== obs for envs that did not finish)
+    int32_t *info;               // [N,2] {reset id after the step, done cause bits}
+    // compact outputs for the host path (os2r_step_host_packed): one byte of reset id per env, and one record
+    // {env index, cause, terminal observation[D]} per FINISHED env appended through an atomic counter
+    uint8_t *reset_id8;          // [N]
+    int32_t *term_count;         // [1], zeroed by the caller before the launch
+    int32_t *term_records;       // [term_cap][D + 2] words
+    int32_t term_cap;
+};
+
 struct StatsDev {                // device-side accumulators (os2r_stats without env_steps)
     unsigned long long episodes, done_task, done_timelimit, nonfinite_resets;
     double sum_return, sum_length;

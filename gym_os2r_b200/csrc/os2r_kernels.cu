@@ -132,9 +132,13 @@ __global__ void __maxnreg__(sizeof(T) == 4 ? OS2R_MAXNREG : 255)
 __global__ void __launch_bounds__(BLOCK, (sizeof(T) == 4 ? OS2R_RESIDENT_THREADS / BLOCK : 1))
 #endif
 step_kernel(const __grid_constant__ ModelDev<T> M, const __grid_constant__ TaskDev K, StateDev<T> S,
-            const float *__restrict__ actions, float *__restrict__ obs, float *__restrict__ reward,
-            uint8_t *__restrict__ done, float *__restrict__ term_obs, int32_t *__restrict__ info,
-            StatsDev *stats) {
+            const __grid_constant__ StepIO IO, StatsDev *stats) {
+    const float *__restrict__ actions = IO.actions;
+    float *__restrict__ obs = IO.obs;
+    float *__restrict__ reward = IO.reward;
+    uint8_t *__restrict__ done = IO.done;
+    float *__restrict__ term_obs = IO.term_obs;
+    int32_t *__restrict__ info = IO.info;
     static_assert(NC <= 3, "class byte: one bit per contact proxy, 2^NC + 1 sort keys");
     const int64_t NE = S.n_envs;
     using SL = ColdSlots<N, NC>;
@@ -244,6 +248,15 @@ step_kernel(const __grid_constant__ ModelDev<T> M, const __grid_constant__ TaskD
     S.a_prev[e] = (T)act.x;
     S.a_prev[NE + e] = (T)act.y;
 
+    if (cause && IO.term_count) {
+        const int k = atomicAdd(IO.term_count, 1);
+        if (k < IO.term_cap) {
+            int32_t *rec = IO.term_records + (int64_t)k * (D + 2);
+            rec[0] = (int32_t)e;
+            rec[1] = cause;
+            for (int c = 0; c < D; ++c) rec[2 + c] = __float_as_int((float)o[c]);
+        }
+    }
     if (cause) {
         atomicAdd(&stats->episodes, 1ull);
         if (cause & 1) atomicAdd(&stats->done_task, 1ull);
@@ -278,6 +291,7 @@ step_kernel(const __grid_constant__ ModelDev<T> M, const __grid_constant__ TaskD
         info[2 * e] = reset_idx;
         info[2 * e + 1] = cause;
     }
+    if (IO.reset_id8) IO.reset_id8[e] = (uint8_t)reset_idx;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -326,8 +340,8 @@ int step_block_threads(int64_t n_envs, int sm_count) {
 }
 
 template <typename T, int N, int BLOCK>
-static cudaError_t launch_step_n(const ModelDev<T> &M, const TaskDev &K, const StateDev<T> &S, const float *actions, float *obs,
-                                 float *reward, uint8_t *done, float *term_obs, int32_t *info, StatsDev *stats, cudaStream_t stream) {
+static cudaError_t launch_step_n(const ModelDev<T> &M, const TaskDev &K, const StateDev<T> &S, const StepIO &io, StatsDev *stats,
+                                 cudaStream_t stream) {
     constexpr size_t smem = step_smem_bytes<T, N, BLOCK>();
     if (smem > 48 * 1024) {
         static bool raised = false;   // per kernel instantiation
@@ -337,22 +351,21 @@ static cudaError_t launch_step_n(const ModelDev<T> &M, const TaskDev &K, const S
             raised = true;
         }
     }
-    step_kernel<T, N, OS2R_NC, BLOCK><<<grid_for(S.n_envs, BLOCK), BLOCK, smem, stream>>>(M, K, S, actions, obs, reward, done, term_obs, info, stats);
+    step_kernel<T, N, OS2R_NC, BLOCK><<<grid_for(S.n_envs, BLOCK), BLOCK, smem, stream>>>(M, K, S, io, stats);
     return cudaGetLastError();
 }
 
 template <typename T>
 cudaError_t launch_step(int n_dof, int n_contacts, int block, const ModelDev<T> &M, const TaskDev &K, const StateDev<T> &S,
-                        const float *actions, float *obs, float *reward, uint8_t *done, float *term_obs,
-                        int32_t *info, StatsDev *stats, cudaStream_t stream) {
+                        const StepIO &io, StatsDev *stats, cudaStream_t stream) {
     if (n_contacts != OS2R_NC) return cudaErrorInvalidValue;
     if (sizeof(T) == 4 && block == OS2R_BLOCK_WIDE) {
         if constexpr (sizeof(T) == 4) {
-            OS2R_DISPATCH_N(n_dof, return (launch_step_n<T, N_, OS2R_BLOCK_WIDE>(M, K, S, actions, obs, reward, done, term_obs, info, stats, stream)));
+            OS2R_DISPATCH_N(n_dof, return (launch_step_n<T, N_, OS2R_BLOCK_WIDE>(M, K, S, io, stats, stream)));
         }
     }
     if (block != OS2R_BLOCK) return cudaErrorInvalidValue;
-    OS2R_DISPATCH_N(n_dof, return (launch_step_n<T, N_, OS2R_BLOCK>(M, K, S, actions, obs, reward, done, term_obs, info, stats, stream)));
+    OS2R_DISPATCH_N(n_dof, return (launch_step_n<T, N_, OS2R_BLOCK>(M, K, S, io, stats, stream)));
     return cudaErrorInvalidValue;
 }
 
@@ -401,8 +414,7 @@ cudaError_t launch_fma_peak(float *out, int blocks, int iters, cudaStream_t stre
 #define OS2R_INSTANTIATE(T)                                                                                   \
     template int step_block_threads<T>(int64_t, int);                                                         \
     template cudaError_t launch_step<T>(int, int, int, const ModelDev<T> &, const TaskDev &, const StateDev<T> &, \
-                                        const float *, float *, float *, uint8_t *, float *, int32_t *,       \
-                                        StatsDev *, cudaStream_t);                                            \
+                                        const StepIO &, StatsDev *, cudaStream_t);                            \
     template cudaError_t launch_reset<T>(int, int, const TaskDev &, const StateDev<T> &, const uint8_t *,     \
                                          float *, cudaStream_t);                                              \
     template cudaError_t launch_init<T>(const TaskDev &, const StateDev<T> &, double, cudaStream_t);          \

@@ -119,6 +119,39 @@ class Engine:
         _capi.check(self.lib.os2r_step_host(self.handle, p(a), p(obs), p(rew), p(done), p(term), p(info)), self.lib)
         return obs, rew, done, term, info
 
+    def step_host_packed(self, actions: np.ndarray, prefix_records: int = None):
+        """numpy in / numpy out at full batch size through ``os2r_step_host_packed``: ONE device-to-host copy into
+        one page-locked block; the returned arrays are views of that block (recycled only once the caller has dropped
+        every view). Returns ``(obs[N,D], reward[N], done[N] bool, reset_id[N] uint8, term_idx[k], term_cause[k],
+        term_obs[k,D])`` where the ``term_*`` arrays describe the k envs that finished an episode in this step."""
+        a = np.ascontiguousarray(actions, dtype=np.float32)
+        if a.shape != (self.n_envs, 2):
+            raise ValueError(f'actions must have shape ({self.n_envs}, 2), got {a.shape}')
+        N, D = self.n_envs, self.obs_dim
+        if prefix_records is None:
+            prefix_records = min(N, max(256, N // 64))
+        L = self._packed_layouts.get(prefix_records) if hasattr(self, '_packed_layouts') else None
+        if L is None:
+            L = _capi.PackedLayout()
+            _capi.check(self.lib.os2r_packed_layout_get(self.handle, int(prefix_records), C.byref(L)), self.lib)
+            self.__dict__.setdefault('_packed_layouts', {})[prefix_records] = L
+        block = self._host_array(('block', prefix_records), (int(L.total_bytes),), torch.uint8)
+        n_term = C.c_int32(0)
+        _capi.check(self.lib.os2r_step_host_packed(self.handle, a.ctypes.data_as(C.c_void_p),
+                                                   block.ctypes.data_as(C.c_void_p), int(prefix_records),
+                                                   C.byref(n_term)), self.lib)
+        obs = block[L.obs:L.obs + N * D * 4].view(np.float32).reshape(N, D)
+        rew = block[L.reward:L.reward + N * 4].view(np.float32)
+        done = block[L.done:L.done + N].view(np.bool_)
+        rid = block[L.reset_id:L.reset_id + N]
+        k, rw = int(n_term.value), int(L.record_words)
+        if k <= prefix_records:
+            rec = block[L.term_records:L.term_records + k * rw * 4].view(np.int32).reshape(k, rw)
+        else:   # rare (e.g. every env hits the TimeLimit in the same step): fetch the full list
+            rec = np.empty((k, rw), dtype=np.int32)
+            _capi.check(self.lib.os2r_fetch_terminal_records(self.handle, 0, k, rec.ctypes.data_as(C.c_void_p)), self.lib)
+        return obs, rew, done, rid, rec[:, 0], rec[:, 1], rec[:, 2:].view(np.float32)
+
     # ------------------------------------------------------------------ state access
     def get_state(self) -> np.ndarray:
         out = np.empty((self.n_envs, self.state_width), dtype=np.float64)

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define OS2R_ABI_VERSION 5
+#define OS2R_ABI_VERSION 6
 
 #define OS2R_MAX_DOF 5
 #define OS2R_MAX_CONTACTS 4
@@ -188,6 +188,30 @@ int32_t os2r_step(os2r_env *env, const float *actions_dev, float *obs_dev, float
  * This is what a numpy-facing caller (VecEnv.step, common/vec_env/vec_env.py:162-174) uses. */
 int32_t os2r_step_host(os2r_env *env, const float *actions, float *obs, float *reward,
                        uint8_t *done, float *terminal_obs, int32_t *info);
+
+/* The numpy-facing step at full batch size: everything a VecEnv.step returns comes back in ONE page-locked host
+ * block through ONE device-to-host copy — obs, reward, done, one byte of reset-orientation id per env, and, instead
+ * of a dense [N, obs_dim] terminal-observation array, one record per env that FINISHED an episode in this step
+ * (info['terminal_observation'] exists only for those, subproc_vec_env.py:17-20). Byte offsets from the block start: */
+typedef struct os2r_packed_layout {
+    int64_t obs;            /* float32 [N, obs_dim]                                                    */
+    int64_t reward;         /* float32 [N]                                                             */
+    int64_t done;           /* uint8   [N] 0/1                                                         */
+    int64_t reset_id;       /* uint8   [N] index into the task's reset_positions after the step        */
+    int64_t term_count;     /* int32   [1] number of envs that finished an episode in this step        */
+    int64_t term_records;   /* int32   [prefix_records][record_words]: {env index, done-cause bits,
+                               terminal observation as float32 bit patterns [obs_dim]}, unordered      */
+    int64_t total_bytes;    /* size of the host block                                                  */
+    int32_t record_words;   /* obs_dim + 2                                                             */
+    int32_t prefix_records; /* records that travel with the first copy (the block holds this many)     */
+} os2r_packed_layout;
+int32_t os2r_packed_layout_get(const os2r_env *env, int32_t prefix_records, os2r_packed_layout *out);
+/* actions[N,2] (host) -> block (host, laid out as above; page-locked memory is written by DMA directly, pageable
+ * memory through the handle's staging block). *n_terminal = number of finished envs; when it exceeds
+ * prefix_records the remaining records are fetched with os2r_fetch_terminal_records before the next step. */
+int32_t os2r_step_host_packed(os2r_env *env, const float *actions, void *block, int32_t prefix_records,
+                              int32_t *n_terminal);
+int32_t os2r_fetch_terminal_records(os2r_env *env, int32_t first, int32_t count, int32_t *records_host);
 
 /* Packed double state [N, os2r_state_width] <-> device SoA (checkpoint/resume + parity tests). */
 int32_t os2r_get_state(os2r_env *env, double *state_host);

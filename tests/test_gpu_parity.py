@@ -321,6 +321,36 @@ def test_step_host_matches_device_step():
     e1.close(); e2.close()
 
 
+def test_packed_host_step_matches_device_step():
+    """os2r_step_host_packed: one D2H block with obs / reward / done / reset-id bytes and one terminal record per
+    finished env. Covers records travelling in the block's prefix and the overflow fetch (every env hits the
+    TimeLimit in the same step, more records than the prefix holds)."""
+    N = 1024
+    task, cm, cfg = make_config('fixed_hip', reward='BalancingV2', auto_reset=True, max_episode_steps=5,
+                                reset_randomized=True, randomize_params=True, reset_positions=('stand', 'lay', 'ground'))
+    for prefix in (16, N):
+        e1 = Engine(cm, cfg, N, seed=4)
+        e2 = Engine(cm, cfg, N, seed=4)
+        e1.reset(); e2.reset()
+        rng = np.random.RandomState(1)
+        finished = 0
+        for t in range(11):
+            a = rng.uniform(-1, 1, (N, 2)).astype(np.float32)
+            o1, r1, d1, i1 = e1.step(torch.as_tensor(a, device='cuda'))
+            o2, r2, d2, rid, t_idx, t_cause, t_obs = e2.step_host_packed(a, prefix_records=prefix)
+            o1, r1, d1, i1 = o1.cpu().numpy(), r1.cpu().numpy(), d1.cpu().numpy().astype(bool), i1.cpu().numpy()
+            np.testing.assert_array_equal(o1, o2); np.testing.assert_array_equal(r1, r2)
+            assert d2.dtype == np.bool_ and np.array_equal(d1, d2) and np.array_equal(i1[:, 0], rid)
+            order = np.argsort(t_idx)
+            assert np.array_equal(t_idx[order], np.flatnonzero(d1))
+            assert np.array_equal(t_cause[order], i1[d1, 1])
+            np.testing.assert_array_equal(t_obs[order], e1.terminal_obs.cpu().numpy()[d1])
+            finished += len(t_idx)
+        assert finished == 2 * N and len(set(rid.tolist())) == 3
+        assert np.array_equal(e1.get_state(), e2.get_state())
+        e1.close(); e2.close()
+
+
 def test_energy_conservation_on_device():
     """Size-independent property: with damping = friction = 0, no torque, no contact, the semi-implicit
     integrator keeps total mechanical energy within O(dt) of its initial value over 500 env steps."""

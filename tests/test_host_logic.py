@@ -208,8 +208,14 @@ def test_custom_reward_subclass_is_flagged_for_torch_evaluation():
 def test_shard_range_and_lazy_infos():
     assert [shard_range(10, r, 4) for r in range(4)] == [(0, 3), (3, 3), (6, 2), (8, 2)]
     assert shard_range(1 << 20, 7, 8) == (7 * 131072, 131072)
-    infos = LazyInfos(['stand', 'lay'], np.array([0, 1, 1]), np.array([False, True, True]),
-                      np.arange(6.0).reshape(3, 2), np.array([0, 1, 2]))
-    assert len(infos) == 3 and infos[0] == {'reset_orientation': 'stand'}
-    assert infos[2]['TimeLimit.truncated'] and infos[1]['terminal_observation'].tolist() == [2.0, 3.0]
-    assert [i['reset_orientation'] for i in infos] == ['stand', 'lay', 'lay']
+    dense = LazyInfos.from_dense(['stand', 'lay'], np.array([0, 1, 1]), np.array([False, True, True]),
+                                 np.arange(6.0).reshape(3, 2), np.array([0, 1, 2]))
+    # the sparse form the packed host step produces: one record per finished env, in any order
+    sparse = LazyInfos(['stand', 'lay'], np.array([0, 1, 1], dtype=np.uint8), np.array([False, True, True]),
+                       np.array([2, 1]), np.array([2, 1]), np.array([[4.0, 5.0], [2.0, 3.0]]))
+    for infos in (dense, sparse):
+        assert len(infos) == 3 and infos[0] == {'reset_orientation': 'stand'}
+        assert infos[2]['TimeLimit.truncated'] and infos[1]['terminal_observation'].tolist() == [2.0, 3.0]
+        assert 'TimeLimit.truncated' not in infos[1] and infos[2]['terminal_observation'].tolist() == [4.0, 5.0]
+        assert [i['reset_orientation'] for i in infos] == ['stand', 'lay', 'lay']
+        assert sorted(infos.terminal_indices.tolist()) == [1, 2]

@@ -12,12 +12,14 @@ envs.reset()
 eng = envs.runtime.engine
 rng = np.random.RandomState(0)
 acts = [rng.uniform(-1, 1, (N, 2)).astype(np.float32) for _ in range(8)]
+for i in range(400): envs.step(acts[i % 8])   # past touchdown: some envs finish every step
 def t(fn, n=200):
     for i in range(5): fn(i)
     t0 = time.perf_counter()
     for i in range(n): fn(i)
     return (time.perf_counter() - t0) / n * 1e6
 print('VecEnv.step(numpy)            us:', t(lambda i: envs.step(acts[i % 8])))
+print('engine.step_host_packed        us:', t(lambda i: eng.step_host_packed(acts[i % 8])))
 print('engine.step_host (obs,rew,done) us:', t(lambda i: eng.step_host(acts[i % 8])))
 print('engine.step_host (+term,+info)  us:', t(lambda i: eng.step_host(acts[i % 8], True, True)))
 a_dev = [torch.as_tensor(a, device='cuda') for a in acts]
@@ -31,3 +33,13 @@ print('pinned H2D + step + pinned D2H obs us:', t(pinned))
 buf = np.empty((N, 8), np.float32)
 print('np.empty((N,8)) + fill        us:', t(lambda i: np.empty((N, 8), np.float32).fill(0)))
 print('memcpy 2MB np                 us:', t(lambda i: np.copyto(buf, pin_o.numpy())))
+pin_acts = [torch.as_tensor(a).pin_memory().numpy() for a in acts]
+print('engine.step_host_packed, pinned actions us:', t(lambda i: eng.step_host_packed(pin_acts[i % 8])))
+blk = torch.empty(3 * 1024 * 1024, dtype=torch.uint8).pin_memory(); dblk = torch.empty(3 * 1024 * 1024, dtype=torch.uint8, device='cuda')
+def d2h(i):
+    blk.copy_(dblk, non_blocking=True); torch.cuda.synchronize()
+print('pinned D2H 3 MB + sync        us:', t(d2h))
+def h2d(i):
+    a_dev[0].copy_(pin_a, non_blocking=True); torch.cuda.synchronize()
+print('pinned H2D 512 KB + sync      us:', t(h2d))
+print('memcpy 512KB np               us:', t(lambda i: np.copyto(pin_a.numpy(), acts[i % 8])))
