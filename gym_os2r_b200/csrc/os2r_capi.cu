@@ -602,8 +602,8 @@ int32_t os2r_kernel_info(const os2r_env *h, int32_t *block_threads, int32_t *gri
     DeviceGuard guard(h->device);
     cudaFuncAttributes a;
     int resident = 0;
-    cudaError_t e = h->precision == 32 ? step_kernel_attributes<float>(h->model.n_dof, h->block, &a, &resident)
-                                       : step_kernel_attributes<double>(h->model.n_dof, h->block, &a, &resident);
+    cudaError_t e = h->precision == 32 ? step_kernel_attributes<float>(h->model.n_dof, h->block, h->m32.any_damping != 0, &a, &resident)
+                                       : step_kernel_attributes<double>(h->model.n_dof, h->block, true, &a, &resident);
     if (e != cudaSuccess) return fail("cudaFuncGetAttributes failed: %s", cudaGetErrorString(e));
     if (block_threads) *block_threads = h->block;
     if (grid_blocks) *grid_blocks = (int32_t)((h->n + h->block - 1) / h->block);

@@ -240,7 +240,7 @@ struct EnvRegs {                 // hot per-thread state
     T gz;                        // gravity z (negative)
 };
 
-template <typename T, int N, int NC, typename ColdT>
+template <typename T, int N, int NC, bool DAMPED, typename ColdT>
 __device__ __forceinline__ void physics_iteration(const ModelDev<T> &M, EnvRegs<T, N> &E, const ColdT &C) {
     using SL = ColdSlots<N, NC>;
     const T dt = M.dt;
@@ -417,7 +417,7 @@ __device__ __forceinline__ void physics_iteration(const ModelDev<T> &M, EnvRegs<
         }
         cholesky(zero, L, Ld);
         T qdd[N];
-        if (M.any_damping) {
+        if (DAMPED) {   // compile-time: the second factorisation is ~1.6 KB of loop body the undamped models never run
             T dd[N], L2[N][N], L2d[N];
 #pragma unroll
             for (int i = 0; i < N; ++i) dd[i] = dt * C(SL::DAMP + i);

@@ -93,26 +93,31 @@ __global__ void __launch_bounds__(OS2R_BLOCK) init_kernel(const __grid_constant_
 template <int BLOCK, int NKEYS>
 __device__ __forceinline__ int sorted_source(int key, int *scratch) {
     constexpr int W = BLOCK / 32;
-    static_assert(NKEYS * W <= 64 && NKEYS * W <= BLOCK, "two counters per lane of warp 0");
-    int *cnt = scratch;              // [NKEYS * W] counts, then exclusive offsets; heavier classes first
-    int *perm = scratch + 64;        // [BLOCK]
+    constexpr int CNT = NKEYS * W;                 // counters, ordered (heavier class first, then warp)
+    constexpr int PER = (CNT + 31) / 32;           // counters scanned by each lane of warp 0
+    constexpr int CPAD = PER * 32;
+    int *cnt = scratch;              // [CPAD] counts, then exclusive offsets
+    int *perm = scratch + CPAD;      // [BLOCK]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid < 64) cnt[tid] = 0;
+    for (int k = tid; k < CPAD; k += BLOCK) cnt[k] = 0;
     __syncthreads();
     const unsigned same = __match_any_sync(0xffffffffu, key);
     const int p = (NKEYS - 1 - key) * W + warp;
     if (lane == __ffs(same) - 1) cnt[p] = __popc(same);
     __syncthreads();
     if (warp == 0) {
-        const int a = cnt[2 * lane], b = cnt[2 * lane + 1];
-        int s = a + b;
+        int v[PER], s = 0;
+#pragma unroll
+        for (int k = 0; k < PER; ++k) { v[k] = cnt[PER * lane + k]; s += v[k]; }
+        const int own = s;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const int t = __shfl_up_sync(0xffffffffu, s, o);
             if (lane >= o) s += t;
         }
-        cnt[2 * lane] = s - a - b;
-        cnt[2 * lane + 1] = s - b;
+        int run = s - own;
+#pragma unroll
+        for (int k = 0; k < PER; ++k) { cnt[PER * lane + k] = run; run += v[k]; }
     }
     __syncthreads();
     perm[cnt[p] + __popc(same & ((1u << lane) - 1u))] = tid;
@@ -125,7 +130,7 @@ __device__ __forceinline__ int sorted_source(int key, int *scratch) {
 // ------------------------------------------------------------------------------------------------
 // the fused step kernel: substeps x physics + observation + reward + done + auto-reset
 // ------------------------------------------------------------------------------------------------
-template <typename T, int N, int NC, int BLOCK>
+template <typename T, int N, int NC, int BLOCK, bool DAMPED>
 #ifdef OS2R_MAXNREG
 __global__ void __maxnreg__(sizeof(T) == 4 ? OS2R_MAXNREG : 255)
 #else
@@ -217,7 +222,7 @@ step_kernel(const __grid_constant__ ModelDev<T> M, const __grid_constant__ TaskD
         // a rolled forward pass that fits the 32 KB cache still lost 12 % without them and 20 % overall to its
         // extra instructions and spills — DESIGN.md section 9).
         __syncthreads();
-        physics_iteration<T, N, NC, Cold<T, BLOCK>>(M, E, C);
+        physics_iteration<T, N, NC, DAMPED, Cold<T, BLOCK>>(M, E, C);
     }
     if (!valid) return;
 
@@ -327,7 +332,7 @@ static inline int grid_for(int64_t n, int block) { return (int)((n + block - 1) 
 
 template <typename T, int N, int BLOCK>
 static constexpr size_t step_smem_bytes() {
-    size_t cold = (size_t)ColdSlots<N, OS2R_NC>::COUNT * BLOCK * sizeof(T), sort = (size_t)(64 + BLOCK) * sizeof(int);
+    size_t cold = (size_t)ColdSlots<N, OS2R_NC>::COUNT * BLOCK * sizeof(T), sort = (size_t)(512 + BLOCK) * sizeof(int);
     return cold > sort ? cold : sort;
 }
 
@@ -339,20 +344,28 @@ int step_block_threads(int64_t n_envs, int sm_count) {
     return OS2R_BLOCK;
 }
 
-template <typename T, int N, int BLOCK>
-static cudaError_t launch_step_n(const ModelDev<T> &M, const TaskDev &K, const StateDev<T> &S, const StepIO &io, StatsDev *stats,
-                                 cudaStream_t stream) {
+template <typename T, int N, int BLOCK, bool DAMPED>
+static cudaError_t launch_step_nd(const ModelDev<T> &M, const TaskDev &K, const StateDev<T> &S, const StepIO &io, StatsDev *stats,
+                                  cudaStream_t stream) {
     constexpr size_t smem = step_smem_bytes<T, N, BLOCK>();
     if (smem > 48 * 1024) {
         static bool raised = false;   // per kernel instantiation
         if (!raised) {
-            cudaError_t e = cudaFuncSetAttribute(step_kernel<T, N, OS2R_NC, BLOCK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            cudaError_t e = cudaFuncSetAttribute(step_kernel<T, N, OS2R_NC, BLOCK, DAMPED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return e;
             raised = true;
         }
     }
-    step_kernel<T, N, OS2R_NC, BLOCK><<<grid_for(S.n_envs, BLOCK), BLOCK, smem, stream>>>(M, K, S, io, stats);
+    step_kernel<T, N, OS2R_NC, BLOCK, DAMPED><<<grid_for(S.n_envs, BLOCK), BLOCK, smem, stream>>>(M, K, S, io, stats);
     return cudaGetLastError();
+}
+template <typename T, int N, int BLOCK>
+static cudaError_t launch_step_n(const ModelDev<T> &M, const TaskDev &K, const StateDev<T> &S, const StepIO &io, StatsDev *stats,
+                                 cudaStream_t stream) {
+    // the fp64 verification build keeps one (damped) instantiation; with zero damping its second factor equals the first
+    if (sizeof(T) == 8 || M.any_damping) return launch_step_nd<T, N, BLOCK, true>(M, K, S, io, stats, stream);
+    if constexpr (sizeof(T) == 4) return launch_step_nd<T, N, BLOCK, false>(M, K, S, io, stats, stream);
+    return cudaErrorInvalidValue;
 }
 
 template <typename T>
@@ -383,26 +396,32 @@ cudaError_t launch_init(const TaskDev &K, const StateDev<T> &S, double nominal_g
     return cudaGetLastError();
 }
 
-template <typename T, int N, int BLOCK>
-static cudaError_t step_attr_n(cudaFuncAttributes *attr, int *blocks_per_sm) {
+template <typename T, int N, int BLOCK, bool DAMPED>
+static cudaError_t step_attr_nd(cudaFuncAttributes *attr, int *blocks_per_sm) {
     constexpr size_t smem = step_smem_bytes<T, N, BLOCK>();
-    cudaError_t e = cudaFuncGetAttributes(attr, step_kernel<T, N, OS2R_NC, BLOCK>);
+    cudaError_t e = cudaFuncGetAttributes(attr, step_kernel<T, N, OS2R_NC, BLOCK, DAMPED>);
     if (e != cudaSuccess) return e;
     if (smem > 48 * 1024) {
-        e = cudaFuncSetAttribute(step_kernel<T, N, OS2R_NC, BLOCK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        e = cudaFuncSetAttribute(step_kernel<T, N, OS2R_NC, BLOCK, DAMPED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, step_kernel<T, N, OS2R_NC, BLOCK>, BLOCK, smem);
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, step_kernel<T, N, OS2R_NC, BLOCK, DAMPED>, BLOCK, smem);
+}
+template <typename T, int N, int BLOCK>
+static cudaError_t step_attr_n(bool damped, cudaFuncAttributes *attr, int *blocks_per_sm) {
+    if (sizeof(T) == 8 || damped) return step_attr_nd<T, N, BLOCK, true>(attr, blocks_per_sm);
+    if constexpr (sizeof(T) == 4) return step_attr_nd<T, N, BLOCK, false>(attr, blocks_per_sm);
+    return cudaErrorInvalidValue;
 }
 
 template <typename T>
-cudaError_t step_kernel_attributes(int n_dof, int block, cudaFuncAttributes *attr, int *blocks_per_sm) {
+cudaError_t step_kernel_attributes(int n_dof, int block, bool damped, cudaFuncAttributes *attr, int *blocks_per_sm) {
     if (sizeof(T) == 4 && block == OS2R_BLOCK_WIDE) {
         if constexpr (sizeof(T) == 4) {
-            OS2R_DISPATCH_N(n_dof, return (step_attr_n<T, N_, OS2R_BLOCK_WIDE>(attr, blocks_per_sm)));
+            OS2R_DISPATCH_N(n_dof, return (step_attr_n<T, N_, OS2R_BLOCK_WIDE>(damped, attr, blocks_per_sm)));
         }
     }
-    OS2R_DISPATCH_N(n_dof, return (step_attr_n<T, N_, OS2R_BLOCK>(attr, blocks_per_sm)));
+    OS2R_DISPATCH_N(n_dof, return (step_attr_n<T, N_, OS2R_BLOCK>(damped, attr, blocks_per_sm)));
     return cudaErrorInvalidValue;
 }
 
@@ -418,7 +437,7 @@ cudaError_t launch_fma_peak(float *out, int blocks, int iters, cudaStream_t stre
     template cudaError_t launch_reset<T>(int, int, const TaskDev &, const StateDev<T> &, const uint8_t *,     \
                                          float *, cudaStream_t);                                              \
     template cudaError_t launch_init<T>(const TaskDev &, const StateDev<T> &, double, cudaStream_t);          \
-    template cudaError_t step_kernel_attributes<T>(int, int, cudaFuncAttributes *, int *);
+    template cudaError_t step_kernel_attributes<T>(int, int, bool, cudaFuncAttributes *, int *);
 OS2R_INSTANTIATE(float)
 OS2R_INSTANTIATE(double)
 

@@ -13,7 +13,9 @@
 #define OS2R_BLOCK_WIDE 224
 #endif
 #define OS2R_RESIDENT_THREADS 448
+#ifndef OS2R_NC
 #define OS2R_NC 3
+#endif
 
 namespace os2r {
 
@@ -28,7 +30,7 @@ cudaError_t launch_reset(int n_dof, int n_contacts, const TaskDev &K, const Stat
 template <typename T>
 cudaError_t launch_init(const TaskDev &K, const StateDev<T> &S, double nominal_gz, cudaStream_t stream);
 template <typename T>
-cudaError_t step_kernel_attributes(int n_dof, int block, cudaFuncAttributes *attr, int *blocks_per_sm);
+cudaError_t step_kernel_attributes(int n_dof, int block, bool damped, cudaFuncAttributes *attr, int *blocks_per_sm);
 cudaError_t launch_fma_peak(float *out, int blocks, int iters, cudaStream_t stream);
 
 }  // namespace os2r

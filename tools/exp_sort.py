@@ -26,6 +26,8 @@ def run(mode='fixed_hip', N=65536, pre=1500, steps=200, iters=None, tol=None, en
         if iters is not None: kw['pgs_iters'] = iters
         if tol is not None: kw['pgs_tol'] = tol
         task, cm, cfg = make_config(mode, reward='BalancingV1' if mode != 'simple' else 'StraightV1', **kw)
+        if os.environ.get('EXP_NC1'):      # I-cache footprint probe: keep only the hip proxy (lib built with -DOS2R_NC=1)
+            cm.struct.n_contacts = 1
         eng = Engine(cm, cfg, N, seed=42)
         eng.reset()
         g = torch.Generator(device='cuda'); g.manual_seed(0)
@@ -34,7 +36,7 @@ def run(mode='fixed_hip', N=65536, pre=1500, steps=200, iters=None, tol=None, en
         for i in range(pre): eng.step(acts[i % P])
         ms = min(timeit(lambda i: eng.step(acts[i % P]), steps) for _ in range(3))
         st = eng.stats()
-        lam = eng.get_state()[:, 3 * cm.n_dof:3 * cm.n_dof + 9:3]
+        lam = eng.get_state()[:, 3 * cm.n_dof:3 * cm.n_dof + 3 * cm.struct.n_contacts:3]
         info = eng.kernel_info()
         eng.close()
     finally:
@@ -73,6 +75,30 @@ if __name__ == '__main__':
         P(run(iters=8, tol=1e-6, env={'OS2R_SORT_MARGIN': -1.0}))
         P(run(iters=8, tol=1e-6, pre=0)); P(run(iters=8, tol=1e-6, pre=300)); P(run(iters=8, tol=1e-6, pre=5000))
         P(run(iters=6, tol=1e-6)); P(run(iters=8, tol=3e-6))
+    if which == 'e':
+        P('lib=' + os.environ.get('OS2R_LIB', 'default'))
+        blk = os.environ.get('EXP_BLOCK')
+        env = {'OS2R_FORCE_BLOCK': blk} if blk else {}
+        P(run(iters=8, tol=1e-6, env=env)); P(run(iters=8, tol=1e-6, pre=0, env=env))
+        P(run(iters=8, tol=1e-6, env=dict(env, OS2R_SORT_MARGIN=-1.0)))
+    if which == 'g':     # strictly contact-free window: steps 5..65 after a reset, repeated
+        P('lib=' + os.environ.get('OS2R_LIB', 'default'))
+        kw = dict(randomize_params=True, randomize_gravity=True, reset_randomized=True, auto_reset=True, max_episode_steps=100000, pgs_iters=8, pgs_tol=1e-6)
+        task, cm, cfg = make_config('fixed_hip', reward='BalancingV1', **kw)
+        if os.environ.get('EXP_NC1'): cm.struct.n_contacts = 1
+        N = 65536
+        eng = Engine(cm, cfg, N, seed=42)
+        g = torch.Generator(device='cuda'); g.manual_seed(0)
+        acts = [(torch.rand((N, 2), device='cuda', generator=g) * 2 - 1) for _ in range(64)]
+        best = 1e9
+        for rep in range(6):
+            eng.reset()
+            for i in range(5): eng.step(acts[i])
+            best = min(best, timeit(lambda i: eng.step(acts[5 + i]), 55))
+        nc = cm.struct.n_contacts
+        lam = eng.get_state()[:, 3 * cm.n_dof:3 * cm.n_dof + 3 * nc:3]
+        P(f'contact-free window: {best*1e3:.1f} us/step; contact frac at the end {(lam>0).mean(0).round(4).tolist()}')
+        eng.close()
     if which in ('all', 'b'):
         for N in (9472, 16384, 33152, 131072):
             P(run(N=N)); P(run(N=N, env={'OS2R_FORCE_BLOCK': 64}))
