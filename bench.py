@@ -133,6 +133,16 @@ def main():
     ap.add_argument('--envs-per-gpu', type=int, default=ENVS_PER_GPU)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()
+    # stdout carries exactly ONE JSON line: anything a library prints there (e.g. the NCCL version banner) is sent
+    # to stderr instead, and the line is written to the saved descriptor at the end
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line):
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + '\n').encode())
+
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
@@ -156,7 +166,7 @@ def main():
                                   'sample': r['sample']},
                     e2e={'value': r['value'], 'unit': 'env-steps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
                     gpu_launches=0)
-        print(json.dumps(line))
+        emit(line)
         return
 
     import numpy as np
@@ -318,7 +328,7 @@ def main():
             r = cpu_reference_run(steps=100, warmup=2, envs_per_core=128)
             line['cpu_baseline'] = {'value': r['value'], 'unit': 'env-steps/s', 'cores': r['cores'], 'kind': 'port',
                                     'sample': r['sample']}
-        print(json.dumps(line))
+        emit(line)
     envs.close()
     if world > 1:
         dist.destroy_process_group()

@@ -39,9 +39,10 @@ def test_every_declared_symbol_is_exported(lib):
 
 def test_ctypes_layout_matches_header():
     """Compile a tiny C program against include/os2r.h and compare sizeof / offsetof with ctypes."""
-    fields = {'os2r_model': (_capi.Model, ['n_dof', 'contact_body', 'tree_R', 'mass', 'inertia', 'contact_pos', 'gravity_z', 'max_torque']),
+    fields = {'os2r_model': (_capi.Model, ['n_dof', 'contact_body', 'tree_R', 'mass', 'inertia', 'contact_pos', 'gravity_z', 'max_torque', 'pgs_tol']),
               'os2r_task_cfg': (_capi.TaskCfg, ['obs_dim', 'obs_kind', 'reset_laying', 'obs_low', 'done_high', 'simple_lo', 'ik_clip', 'grav_std']),
-              'os2r_stats': (_capi.Stats, ['env_steps', 'sum_length'])}
+              'os2r_stats': (_capi.Stats, ['env_steps', 'sum_length']),
+              'os2r_packed_layout': (_capi.PackedLayout, ['obs', 'reset_id', 'term_records', 'total_bytes', 'record_words', 'prefix_records'])}
     prints = []
     for sname, (_, fl) in fields.items():
         prints.append(f'printf("%zu\\n", sizeof({sname}));')
@@ -74,6 +75,10 @@ def test_create_rejects_bad_arguments(lib):
     assert b'precision' in lib.os2r_last_error()
     assert lib.os2r_step(None, None, None, None, None, None, None, None) != 0
     assert b'null handle' in lib.os2r_last_error()
+    assert lib.os2r_step_host_packed(None, None, None, 0, None) != 0 and b'null argument' in lib.os2r_last_error()
+    bad = type(cm.struct)(); C.memmove(C.byref(bad), C.byref(cm.struct), C.sizeof(bad)); bad.pgs_tol = -1.0
+    assert lib.os2r_create(C.byref(bad), C.byref(cfg), 8, 0, 0, 1, 32, C.byref(h)) != 0
+    assert b'pgs_tol' in lib.os2r_last_error()
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason='checks the no-GPU failure mode')
