@@ -321,14 +321,15 @@ static void invert_spd(int n, double A[NMAX][NMAX], double B[NMAX][NMAX]) {
     for (int i = 0; i < n; ++i) for (int j = 0; j < n; ++j) B[i][j] = W[i][n + j];
 }
 
-/* Projected Gauss-Seidel, fixed row order, at most `sweeps` sweeps. With tol > 0 the iteration of this
- * env ends after the first sweep whose velocity change is <= tol in the kinetic-energy norm
- * sqrt(dv^T M dv) (the kernel measures the same quantity as |dz| in its Cholesky-whitened coordinates). */
+/* Projected Gauss-Seidel, fixed row order, at most `sweeps` sweeps. The iteration of this env ends after
+ * the first sweep whose velocity change is <= tol in the kinetic-energy norm sqrt(dv^T M dv) (the kernel
+ * measures the same quantity as |dz| in its Cholesky-whitened coordinates); tol = 0 ends it only when a
+ * sweep left the velocity exactly unchanged (os2r_model.pgs_tol, include/os2r.h). */
 static void pgs_sweeps(const os2r_model *M, const env_params *P, const constraint_set *S,
                        double Minv[NMAX][NMAX], double *v, double *lam, int sweeps, double tol) {
     int n = M->n_dof, it;
     double Mass[NMAX][NMAX];
-    if (tol > 0) invert_spd(n, Minv, Mass);
+    invert_spd(n, Minv, Mass);
     for (it = 0; it < sweeps; ) {
         double v0[NMAX];
         for (int i = 0; i < n; ++i) v0[i] = v[i];
@@ -351,11 +352,9 @@ static void pgs_sweeps(const os2r_model *M, const env_params *P, const constrain
             lam[r] = nl;
         }
         ++it;
-        if (tol > 0) {
-            double e2 = 0;
-            for (int i = 0; i < n; ++i) for (int j = 0; j < n; ++j) e2 += (v[i] - v0[i]) * Mass[i][j] * (v[j] - v0[j]);
-            if (e2 <= tol * tol) break;
-        }
+        double e2 = 0;
+        for (int i = 0; i < n; ++i) for (int j = 0; j < n; ++j) e2 += (v[i] - v0[i]) * Mass[i][j] * (v[j] - v0[j]);
+        if (e2 <= tol * tol) break;
     }
     __atomic_fetch_add(&g_sweep_hist[it < 64 ? it : 64], 1, __ATOMIC_RELAXED);
 }

@@ -149,3 +149,61 @@ def test_fixed_sweeps_track_converged_lcp():
     ref = roll(4000, 1e-16)
     assert np.abs(roll(8, 0.0) - ref).max() < 2e-3      # ~30 steps after touchdown
     assert np.abs(roll(8, 0.0) - ref).max() < np.abs(roll(2, 0.0) - ref).max()
+
+
+def test_sweep_tolerance_rule():
+    """The per-env sweep exit (os2r_model.pgs_tol): a sweep that moved the velocity by <= tol in the kinetic-energy
+    norm ends the iteration. Checked on the oracle: (i) contact-free, the production tolerance changes nothing at all
+    (saturated / sticking joint friction converges in the first sweep); (ii) in contact, it costs no accuracy against
+    fully converged sweeps compared with always running the cap; (iii) it removes most sweeps; (iv) the measure is
+    the energy norm: the inverse the rule uses reproduces the independent numpy mass matrix."""
+    import ctypes as C
+    lib = oracle.lib()
+    hist = (C.c_longlong * 65)()
+
+    def sweeps_done():
+        lib.oracle_sweep_histogram(hist, 1)
+        h = np.array(hist[:])
+        return (h * np.arange(65)).sum(), h.sum()
+
+    # (i) contact-free: `simple` never touches the ground
+    task, cm, cfg = make_config('simple', reward='StraightV1')
+    m, n = cm.struct, cm.n_dof
+    p = oracle.nominal_params(m)
+    rng = np.random.RandomState(2)
+    q, v, lam = rng.uniform(-1, 1, n), rng.uniform(-2, 2, n), np.zeros(n + 9)
+    a = np.array([0.3, -0.2])
+    out_fixed = oracle.substeps(m, p, q, v, lam, a, 500, sweeps=8, tol=0.0)
+    sweeps_done()
+    out_tol = oracle.substeps(m, p, q, v, lam, a, 500, sweeps=8, tol=1e-6)
+    total, iters = sweeps_done()
+    assert np.array_equal(out_fixed[0], out_tol[0]) and np.array_equal(out_fixed[1], out_tol[1])
+    assert iters == 500 and total <= 2 * iters
+
+    # (ii)/(iii) with contact: dropped fixed_hip monopod, 120 env steps (touchdown at ~90)
+    task, cm, cfg = make_config('fixed_hip', reward='BalancingV1')
+    m, n = cm.struct, cm.n_dof
+    p = oracle.nominal_params(m)
+    q0 = np.zeros(n)
+    q0[cm.dof_of('planarizer_pitch_joint')], q0[cm.dof_of('hip_joint')], q0[cm.dof_of('knee_joint')] = 0.15, 0.2861, -0.5877
+    acts = 0.1 * np.random.RandomState(5).uniform(-1, 1, (120, 2))
+
+    def roll(sweeps, tol):
+        q, v, lam = q0.copy(), np.zeros(n), np.zeros(n + 9)
+        for a in acts:
+            q, v, lam = oracle.substeps(m, p, q, v, lam, a, 10, sweeps=sweeps, tol=tol)
+        return q
+    ref = roll(4000, 1e-16)
+    sweeps_done()
+    e_fixed = np.abs(roll(8, 0.0) - ref).max()
+    total_fixed, iters = sweeps_done()
+    e_tol = np.abs(roll(8, 1e-6) - ref).max()
+    total_tol, iters2 = sweeps_done()
+    assert iters == iters2 == 1200 and total_fixed <= 8 * iters
+    assert e_tol < 2e-3 and e_tol < 2 * e_fixed + 1e-6, (e_tol, e_fixed)
+    assert total_tol < total_fixed, (total_tol, total_fixed)   # tol 0 already stops at exact fixed points (no contact)
+
+    # (iv) Minv @ M_numpy = I: the matrix the rule inverts is the inverse of the true mass matrix
+    qq = rng.uniform(-1, 1, n)
+    _, Minv, _, _ = oracle.dynamics_debug(m, p, qq, np.zeros(n), np.zeros(2))
+    np.testing.assert_allclose(Minv @ _mass_matrix_numpy(cm, p, qq), np.eye(n), atol=1e-9)
