@@ -472,6 +472,47 @@ def test_production_sweep_tolerance_agrees_with_oracle():
     eng.close()
 
 
+@pytest.mark.parametrize('N', [1, 33, 65, 33152 + 37, 1 << 20])
+def test_ragged_tiny_and_maximum_batches(N):
+    """Edge sizes: a single env, batches that do not fill a warp / a 64-thread block / a 224-thread block (the threads
+    past the end shadow the last env and sort last), and the 1 048 576 envs of BASELINE config 4 on ONE GPU. Whatever
+    the batch, env g computes the same thing: the first envs and the last env are re-run in engines of their own
+    (first_env_id = g) and must match bit for bit, contacts included (`ground` reset: the foot starts 3 mm up)."""
+    T = 100 if N < (1 << 20) else 6         # `ground` envs touch down after ~25 steps; TimeLimit resets at 45 and 90
+    task, cm, cfg = make_config('fixed_hip', reward='BalancingV1', reset_positions=('ground', 'lay'), auto_reset=True,
+                                max_episode_steps=45, reset_randomized=True, randomize_params=True,
+                                randomize_gravity=True, pgs_tol=1e-6)
+    g = torch.Generator(device='cuda'); g.manual_seed(N % 1000)
+    acts = [torch.rand((N, 2), device='cuda', generator=g) * 2 - 1 for _ in range(T)]
+
+    n = cm.n_dof
+
+    def run(first, count, watch=False):
+        eng = Engine(cm, cfg, count, seed=11, first_env_id=first)
+        eng.reset()
+        touched = False
+        for t in range(T):
+            obs, rew, done, info = eng.step(acts[t][first:first + count].contiguous())
+            if watch and t % 5 == 4:
+                touched |= bool((eng.get_state()[:, 3 * n:3 * n + 9:3] > 0).any())
+        out = (eng.get_state(), obs.cpu().numpy().copy(), rew.cpu().numpy().copy(), eng.stats()['episodes'],
+               eng.kernel_info()['block_threads'], touched)
+        eng.close()
+        return out
+
+    full = run(0, N, watch=33 <= N < (1 << 20))
+    assert full[4] == (224 if N >= 148 * 224 else 64)
+    assert np.isfinite(full[0]).all() and full[3] == N * (T // 45)
+    if 33 <= N < (1 << 20):
+        assert full[5]                                             # some proxy pressed on the ground along the way
+    head = min(N, 40)
+    for first, count in ((0, head), (N - 1, 1)):
+        part = run(first, count)
+        assert np.array_equal(part[0], full[0][first:first + count])
+        assert np.array_equal(part[1], full[1][first:first + count])
+        assert np.array_equal(part[2], full[2][first:first + count])
+
+
 def test_contact_rollout_statistics_match_oracle():
     """Contact config: after touchdown trajectories are chaotic, so compare distributions: touchdown step and
     20-step return of a dropped monopod agree between kernel and oracle (documented tolerance: +-2 steps,
