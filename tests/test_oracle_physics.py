@@ -207,3 +207,55 @@ def test_sweep_tolerance_rule():
     qq = rng.uniform(-1, 1, n)
     _, Minv, _, _ = oracle.dynamics_debug(m, p, qq, np.zeros(n), np.zeros(2))
     np.testing.assert_allclose(Minv @ _mass_matrix_numpy(cm, p, qq), np.eye(n), atol=1e-9)
+
+
+def test_converged_sweeps_solve_the_boxed_lcp():
+    """Solver-independent check of the constraint stage: run the oracle's sweeps to convergence from random
+    penetrating states and verify the KKT conditions of the boxed LCP DART poses (the problem its Dantzig solver
+    answers exactly) with matrices rebuilt here in numpy — w = J (v* + Minv J^T lam) - target + cfm A_rr lam_r must be
+    >= 0 where lam sits on its lower bound, <= 0 on its upper bound, and 0 in between; bounds: joint friction
+    +-f dt, normal [0, inf), tangents +-mu lam_n."""
+    task, cm, cfg = make_config('fixed_hip', reward='BalancingV1')
+    m, n, nc = cm.struct, cm.n_dof, cm.struct.n_contacts
+    p = oracle.nominal_params(m)
+    p[2 * n:3 * n] = [0.02, 0.03, 0.015, 0.04]          # joint friction N m
+    mu = p[3 * n:3 * n + nc]
+    rng = np.random.RandomState(8)
+    checked_contacts = 0
+    for trial in range(12):
+        q = np.array([rng.uniform(-0.3, 0.3), rng.uniform(-0.05, -0.02), rng.uniform(0.6, 1.4), rng.uniform(-2.6, -1.8)])
+        v = rng.normal(0, 1.0, n)
+        a = rng.uniform(-1, 1, 2)
+        qdd, Minv, depth, J = oracle.dynamics_debug(m, p, q, v, a)
+        act = np.repeat(depth > 0, 3)
+        rows = np.concatenate([np.ones(n, bool), act])
+        vstar = v + m.dt * qdd
+        # one physics iteration with (practically) converged sweeps, cold start
+        q1, v1, lam = oracle.substeps(m, p, q, v, np.zeros(n + 3 * nc), a, 1, sweeps=20000, tol=1e-18)
+        np.testing.assert_allclose(v1, vstar + Minv @ J.T @ lam, atol=1e-12)        # impulses act through plain Minv
+        np.testing.assert_allclose(q1, q + m.dt * v1, atol=1e-15)                   # semi-implicit position update
+        A = J @ Minv @ J.T
+        cfm = np.concatenate([np.full(n, m.cfm_joint), np.full(3 * nc, m.cfm_contact)])
+        target = np.zeros(n + 3 * nc)
+        target[n::3] = np.minimum(np.maximum(depth, 0) * m.erp / m.dt, m.max_erv)
+        w = J @ v1 - target + cfm * np.diag(A) * lam
+        lo, hi = np.zeros_like(lam), np.zeros_like(lam)
+        hi[:n] = p[2 * n:3 * n] * m.dt; lo[:n] = -hi[:n]
+        for c in range(nc):
+            lo[n + 3 * c], hi[n + 3 * c] = 0.0, np.inf
+            hi[n + 3 * c + 1:n + 3 * c + 3] = mu[c] * lam[n + 3 * c]
+            lo[n + 3 * c + 1:n + 3 * c + 3] = -mu[c] * lam[n + 3 * c]
+        scale = np.abs(J @ vstar).max() + 1e-3
+        for r in np.flatnonzero(rows):
+            at_lo, at_hi = lam[r] <= lo[r] + 1e-15, lam[r] >= hi[r] - 1e-15
+            if at_lo and at_hi:
+                continue                                    # degenerate box (mu * 0): any w is admissible
+            if at_lo:
+                assert w[r] >= -1e-9 * scale, (trial, r, w[r])
+            elif at_hi:
+                assert w[r] <= 1e-9 * scale, (trial, r, w[r])
+            else:
+                assert abs(w[r]) <= 1e-9 * scale, (trial, r, w[r], lam[r], lo[r], hi[r])
+        assert np.all(lam[~rows] == 0)
+        checked_contacts += int((lam[n::3] > 0).sum())
+    assert checked_contacts >= 10
