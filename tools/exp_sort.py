@@ -99,6 +99,10 @@ if __name__ == '__main__':
         lam = eng.get_state()[:, 3 * cm.n_dof:3 * cm.n_dof + 3 * nc:3]
         P(f'contact-free window: {best*1e3:.1f} us/step; contact frac at the end {(lam>0).mean(0).round(4).tolist()}')
         eng.close()
+    if which == 'h':     # BASELINE config 4: free_hip, production tolerance
+        P(run(mode='free_hip', iters=8, tol=1e-6)); P(run(mode='free_hip', iters=8, tol=1e-6, N=131072, pre=800))
+        P(run(mode='free_hip', iters=8, tol=1e-6, pre=0))
+        P(run(mode='fixed', iters=8, tol=1e-6, pre=1000)); P(run(mode='simple', iters=8, tol=1e-6, pre=100))
     if which in ('all', 'b'):
         for N in (9472, 16384, 33152, 131072):
             P(run(N=N)); P(run(N=N, env={'OS2R_FORCE_BLOCK': 64}))
