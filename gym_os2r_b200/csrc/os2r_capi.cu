@@ -280,6 +280,10 @@ int set_params_impl(os2r_env *h, StateDev<T> &S, const double *in) {
         for (int c = 0; c < nc; ++c) mu[c * N + e] = row[3 * n + c];
         gz[e] = row[3 * n + nc];
     }
+    // a damping written from outside turns on the implicit-damping factorisation even for a model whose nominal
+    // damping is zero (the step kernel is compiled with and without it, os2r_kernels.cu: DAMPED)
+    for (size_t i = 0; i < dm.size(); ++i)
+        if (dm[i] != 0.0) { h->m32.any_damping = 1; h->m64.any_damping = 1; break; }
     return put_real(h, S.mass_scale, n, ms) || put_real(h, S.damping, n, dm) || put_real(h, S.friction, n, fr) ||
            put_real(h, S.mu, nc, mu) || put_real(h, S.gravity_z, 1, gz);
 }

@@ -94,6 +94,29 @@ def test_single_step_parity(mode, contact):
         eng.close()
 
 
+def test_damping_written_through_set_params_is_implicit():
+    """fixed_hip carries no joint damping, so its step kernel is the instantiation without the second (implicit
+    damping) factorisation; a damping written through os2r_set_params must switch to the damped one and match the
+    oracle's implicit treatment (a purely explicit -d*qd would differ at first order in dt*d/M)."""
+    N = 256
+    rng = np.random.RandomState(21)
+    for prec, tq, tv in ((64, 1e-11, 1e-9), (32, 5e-7, 5e-4)):
+        task, cm, cfg, eng, orc = _pair('fixed_hip', N, prec)
+        n = cm.n_dof
+        assert not np.any(np.array(cm.struct.damping[:n]))
+        eng.set_state(_random_state(cm, N, rng, False))
+        params = eng.get_params()
+        params[:, n:2 * n] = rng.uniform(0.02, 0.2, (N, n))     # large enough that explicit vs implicit is visible
+        eng.set_params(params)
+        orc.state[:] = eng.get_state(); orc.params[:] = eng.get_params()
+        a = rng.uniform(-1, 1, (N, 2)).astype(np.float32)
+        eng.step(torch.as_tensor(a, device='cuda'))
+        orc.step(a.astype(np.float64))
+        eq, ev = _err(eng, orc, n)
+        assert eq < tq and ev < tv, (prec, eq, ev)
+        eng.close()
+
+
 def test_contact_free_trajectory_simple():
     """BASELINE config 2a: `simple` mode (2 DoF, never touches the ground), sinusoidal actions A = 0.1,
     f = (1.0, 1.7) Hz, random phases, 1000 env steps: fp32 kernel within 1e-4 rad / 1e-3 rad/s of the oracle."""
