@@ -134,6 +134,29 @@ __device__ __forceinline__ double fmax_t(double a, double b) { return fmax(a, b)
 // calls this once per joint; one shared copy keeps the loop body inside the instruction cache.
 template <typename T>
 struct SinCos { T s, c; };       // returned by value: stays in registers across the call (pointers would go via the stack)
+// fp32 sin/cos for the forward pass, inlined and evaluated for all joints of an env side by side (independent
+// chains the compiler interleaves; the out-of-line sincosf call per joint was 7 % of the instructions but 13 % of the
+// stall samples of the contact-free step: call overhead, one chain at a time, and its far-away code was refetched
+// by every call). Three-term Cody-Waite reduction by pi/2 (the same scheme as the library's fast path, exact enough for
+// |x| < 1e5; beyond that the library routine is called) and the cephes minimax polynomials on [-pi/4, pi/4]: <= 1 ulp.
+__device__ __forceinline__ void sincos_fast(float x, float *sn, float *cs) {
+    const float j = rintf(x * 0.636619772367581343f);          // x * 2/pi
+    float r = fmaf(j, -1.57079601287841796875f, x);            // pi/2 split in three parts
+    r = fmaf(j, -3.1391647326017846353352069854736328125e-7f, r);
+    r = fmaf(j, -5.390302529957764765544681040410068817436695098876953125e-15f, r);
+    const int q = (int)j;
+    const float r2 = r * r;
+    float ps = fmaf(r2, -1.9515295891e-4f, 8.3321608736e-3f);
+    ps = fmaf(ps, r2, -1.6666654611e-1f);
+    const float sr = fmaf(ps * r2, r, r);                      // sin r
+    float pc = fmaf(r2, 2.443315711809948e-5f, -1.388731625493765e-3f);
+    pc = fmaf(pc, r2, 4.166664568298827e-2f);
+    const float cr = fmaf(pc * r2, r2, fmaf(r2, -0.5f, 1.0f)); // cos r
+    const float s0 = (q & 1) ? cr : sr, c0 = (q & 1) ? sr : cr;
+    *sn = (q & 2) ? -s0 : s0;
+    *cs = ((q + 1) & 2) ? -c0 : c0;
+}
+
 template <typename T>
 __device__ __noinline__ SinCos<T> joint_sincos(T hi, T lo) {
     T s, c;
@@ -260,6 +283,34 @@ __device__ __forceinline__ void physics_iteration(const ModelDev<T> &M, EnvRegs<
 #pragma unroll
         for (int k = 0; k <= j; ++k) Mm[j][k] = 0;
     }
+    T sn[N], cs[N];      // sin / cos of every joint angle (hi + lo)
+    if (sizeof(T) == 4) {
+        bool big = false;
+#pragma unroll
+        for (int i = 0; i < N; ++i) big = big || !(fabsf((float)E.q_hi[i]) < 1.0e5f);
+        if (big) {       // a joint that has turned > 15 000 revolutions (or is non-finite): library range reduction
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                const SinCos<T> sc = joint_sincos<T>(E.q_hi[i], C(SL::QLO + i));
+                sn[i] = sc.s; cs[i] = sc.c;
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                float s, c;
+                sincos_fast((float)E.q_hi[i], &s, &c);
+                const T lo = C(SL::QLO + i);
+                sn[i] = (T)s + lo * (T)c;
+                cs[i] = (T)c - lo * (T)s;
+            }
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            const SinCos<T> sc = joint_sincos<T>(E.q_hi[i], T(0));
+            sn[i] = sc.s; cs[i] = sc.c;
+        }
+    }
     {
         T R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
         T p[3] = {0, 0, 0};
@@ -290,8 +341,7 @@ __device__ __forceinline__ void physics_iteration(const ModelDev<T> &M, EnvRegs<
                     for (int c = 0; c < 3; ++c)
                         A[3 * r + c] = R[3 * r] * tR[c] + R[3 * r + 1] * tR[3 + c] + R[3 * r + 2] * tR[6 + c];
             }
-            const SinCos<T> sc = joint_sincos<T>(E.q_hi[i], sizeof(T) == 4 ? C(SL::QLO + i) : T(0));
-            const T s = sc.s, c = sc.c;
+            const T s = sn[i], c = cs[i];
 #pragma unroll
             for (int r = 0; r < 3; ++r) {
                 const T a1 = A[3 * r + 1], a2 = A[3 * r + 2];
