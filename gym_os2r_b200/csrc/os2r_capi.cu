@@ -97,6 +97,8 @@ void build_model_dev(const os2r_model &m, ModelDev<T> &d) {
     d.max_erv = (T)m.max_erv;
     d.cfm_contact = (T)m.cfm_contact;
     d.cfm_joint = (T)m.cfm_joint;
+    d.cfm1_contact = (T)(1.0 + m.cfm_contact); d.cfm1_joint = (T)(1.0 + m.cfm_joint);
+    d.kc1 = (T)1 / d.cfm1_contact; d.kj1 = (T)1 / d.cfm1_joint;    // same rounding as the division the kernel used to do
     d.max_torque[0] = (T)m.max_torque[0];
     d.max_torque[1] = (T)m.max_torque[1];
     d.hip_dof = m.role_dof[OS2R_ROLE_HIP];

@@ -44,6 +44,8 @@ struct ModelDev {
     T contact_pos[OS2R_MAX_CONTACTS][3];
     T contact_radius[OS2R_MAX_CONTACTS];
     T dt, erp_over_dt, max_erv, cfm_contact, cfm_joint;
+    T cfm1_contact, cfm1_joint;  // 1 + cfm
+    T kc1, kj1;                  // 1 / (1 + cfm)  (host-side: an IEEE division per physics iteration otherwise)
     T pgs_tol2;                  // squared energy-norm tolerance of the sweeps (os2r_model.pgs_tol)
     T sort_margin;               // ground clearance below which a contact proxy counts as "near" (lane sorting hint)
     T max_torque[2];
@@ -509,7 +511,7 @@ __device__ __forceinline__ void physics_iteration(const ModelDev<T> &M, EnvRegs<
             a += Gj[r][k] * Gj[r][k];
             b += Gj[r][k] * z0[k];
         }
-        Aj[r] = rcp_t(a * (T(1) + M.cfm_joint));
+        Aj[r] = rcp_t(a * M.cfm1_joint);
         bj[r] = b;
         jact[r] = C(SL::FRIC + r) > T(0);
         if (jact[r]) {   // warm start
@@ -553,7 +555,7 @@ __device__ __forceinline__ void physics_iteration(const ModelDev<T> &M, EnvRegs<
                     a += Gc[c][d][k] * Gc[c][d][k];
                     b += Gc[c][d][k] * z0[k];
                 }
-                Ac[c][d] = rcp_t(a * (T(1) + M.cfm_contact));
+                Ac[c][d] = rcp_t(a * M.cfm1_contact);
                 bc[c][d] = b;
                 const T l = C(SL::LAM + N + 3 * c + d);   // warm start
 #pragma unroll
@@ -572,7 +574,7 @@ __device__ __forceinline__ void physics_iteration(const ModelDev<T> &M, EnvRegs<
     // |dz| = sqrt(dv^T M dv) is <= pgs_tol (tol 0: only when the sweep left z bit-for-bit unchanged, the typical
     // case being saturated joint friction without contact). The decision uses the lane's own data only, so a
     // result never depends on which other envs share the warp; the warp leaves the loop when its last lane does.
-    const T kj1 = T(1) / (T(1) + M.cfm_joint), kc1 = T(1) / (T(1) + M.cfm_contact);   // 1 - k
+    const T kj1 = M.kj1, kc1 = M.kc1;   // 1 - k
     const T tol2 = M.pgs_tol2;
 #pragma unroll 1
     for (int it = 0; it < M.pgs_iters; ++it) {

@@ -155,6 +155,24 @@ step_kernel(const __grid_constant__ ModelDev<T> M, const __grid_constant__ TaskD
     const int64_t window = (int64_t)blockIdx.x * BLOCK;
     const bool nominal_valid = window + threadIdx.x < NE;
     const int key = nominal_valid ? 1 + (int)(__ldcg(S.cls + window + threadIdx.x) & ((1u << NC) - 1u)) : 0;
+    // While the class byte travels and the block sorts, pull the window's state lines towards the L2: which env a
+    // thread will step is not known yet, but it is one of this window's, so the DRAM latency of the prologue loads
+    // overlaps the sort instead of following it.
+    if (nominal_valid) {
+        const int64_t en = window + threadIdx.x;
+        auto pf = [](const void *ptr) { asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr)); };
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            pf(S.q_hi + i * NE + en); pf(S.qd + i * NE + en); pf(S.q_lo + i * NE + en); pf(S.qd_lo + i * NE + en);
+            pf(S.mass_scale + i * NE + en); pf(S.damping + i * NE + en); pf(S.friction + i * NE + en);
+        }
+#pragma unroll
+        for (int r = 0; r < ROWS; ++r) pf(S.lam + r * NE + en);
+#pragma unroll
+        for (int c = 0; c < NC; ++c) pf(S.mu + c * NE + en);
+        pf(S.gravity_z + en); pf(S.a_prev + en); pf(S.a_prev + NE + en); pf(S.steps + en); pf(S.reset_id + en);
+        pf(S.ret + en); pf(reinterpret_cast<const float2 *>(IO.actions) + en);
+    }
     const int src = sorted_source<BLOCK, (1 << NC) + 1>(key, reinterpret_cast<int *>(smem_raw));
     const int64_t e_raw = window + src;
     const bool valid = e_raw < NE;
