@@ -20,6 +20,8 @@ def t(fn, n=200):
     return (time.perf_counter() - t0) / n * 1e6
 print('VecEnv.step(numpy)            us:', t(lambda i: envs.step(acts[i % 8])))
 print('engine.step_host_packed        us:', t(lambda i: eng.step_host_packed(acts[i % 8])))
+if os.environ.get('E2E_SHORT'):
+    sys.exit(0)
 print('engine.step_host (obs,rew,done) us:', t(lambda i: eng.step_host(acts[i % 8])))
 print('engine.step_host (+term,+info)  us:', t(lambda i: eng.step_host(acts[i % 8], True, True)))
 a_dev = [torch.as_tensor(a, device='cuda') for a in acts]
