@@ -13,7 +13,7 @@ MAX_OBS = 12
 MAX_RESETS = 8
 MAX_ROWS = MAX_DOF + 3 * MAX_CONTACTS
 N_ROLES = 5
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 ROLE_HIP, ROLE_KNEE, ROLE_PITCH, ROLE_YAW, ROLE_BOOM_CONNECTOR = range(5)
 ROLE_OF_JOINT = {
@@ -112,6 +112,8 @@ SYMBOLS = {
     'os2r_step_host': (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     'os2r_packed_layout_get': (_i32, [_vp, _i32, C.POINTER(PackedLayout)]),
     'os2r_step_host_packed': (_i32, [_vp, _vp, _vp, _i32, C.POINTER(_i32)]),
+    'os2r_step_host_packed_begin': (_i32, [_vp, _vp, _vp, _i32]),
+    'os2r_step_host_packed_end': (_i32, [_vp, C.POINTER(_i32)]),
     'os2r_fetch_terminal_records': (_i32, [_vp, _i32, _i32, _vp]),
     'os2r_get_state': (_i32, [_vp, _vp]),
     'os2r_set_state': (_i32, [_vp, _vp]),

@@ -78,7 +78,10 @@ class CudaVecEnv:
     def step_async(self, actions):
         custom = self.runtime._cfg.reward_id == 0
         if self.output == 'numpy' and not custom:
-            self._pending = ('host', np.asarray(actions, dtype=np.float32))   # runs in step_wait (synchronous API)
+            # numpy in / numpy out through the C-ABI host entry points: the actions are staged and H2D + kernel + ONE D2H
+            # into a pinned block are enqueued now; step_wait only waits (the caller may do other work in between)
+            self.runtime.engine.step_host_packed_begin(np.asarray(actions, dtype=np.float32))
+            self._pending = ('host', None)
         else:
             self._pending = ('device', self.env.step(actions))                # enqueued on the current stream
         self.waiting = True
@@ -88,8 +91,7 @@ class CudaVecEnv:
         self._pending, self.waiting = None, False
         names = self.runtime.task.reset_positions
         if kind == 'host':
-            # numpy in / numpy out through the C-ABI host entry point: H2D, kernel, ONE D2H into a pinned block
-            obs, rew, done, rid, t_idx, t_cause, t_obs = self.runtime.engine.step_host_packed(payload)
+            obs, rew, done, rid, t_idx, t_cause, t_obs = self.runtime.engine.step_host_packed_end()
             return obs, rew, done, LazyInfos(names, rid, done, t_idx, t_cause, t_obs)
         obs, rew, done, info = payload
         if self.output == 'torch':

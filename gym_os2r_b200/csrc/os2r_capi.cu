@@ -152,6 +152,9 @@ struct os2r_env {
     // single-block I/O of os2r_step_host_packed
     unsigned char *dev_block = nullptr, *pin_block = nullptr;
     size_t pin_block_bytes = 0;
+    bool packed_pending = false, packed_block_pinned = false;   // a packed step enqueued by ..._begin, not yet completed
+    void *packed_block = nullptr;
+    int32_t packed_prefix = 0;
     int64_t launches = 0;
     uint64_t env_steps = 0;
 };
@@ -498,9 +501,10 @@ int32_t os2r_packed_layout_get(const os2r_env *h, int32_t prefix_records, os2r_p
     return 0;
 }
 
-int32_t os2r_step_host_packed(os2r_env *h, const float *actions, void *block, int32_t prefix_records, int32_t *n_terminal) {
-    if (!h || !actions || !block) return fail("os2r_step_host_packed: null argument");
-    if (prefix_records < 0 || prefix_records > h->n) return fail("os2r_step_host_packed: prefix_records must be in [0, n_envs]");
+int32_t os2r_step_host_packed_begin(os2r_env *h, const float *actions, void *block, int32_t prefix_records) {
+    if (!h || !actions || !block) return fail("os2r_step_host_packed_begin: null argument");
+    if (prefix_records < 0 || prefix_records > h->n) return fail("os2r_step_host_packed_begin: prefix_records must be in [0, n_envs]");
+    if (h->packed_pending) return fail("os2r_step_host_packed_begin: the previous packed step has not been completed (call os2r_step_host_packed_end)");
     DeviceGuard guard(h->device);
     if (ensure_host_io(h)) return 1;
     const int64_t N = h->n;
@@ -531,10 +535,29 @@ int32_t os2r_step_host_packed(os2r_env *h, const float *actions, void *block, in
     if (do_step(h, io, st)) return 1;
     unsigned char *dst = pb ? (unsigned char *)block : h->pin_block;
     CK(cudaMemcpyAsync(dst, h->dev_block, (size_t)L.total_bytes, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-    if (!pb) memcpy(block, h->pin_block, (size_t)L.total_bytes);
-    if (n_terminal) *n_terminal = *(const int32_t *)((const unsigned char *)block + L.term_count);
+    h->packed_pending = true;
+    h->packed_block = block;
+    h->packed_block_pinned = pb;
+    h->packed_prefix = prefix_records;
     return 0;
+}
+
+int32_t os2r_step_host_packed_end(os2r_env *h, int32_t *n_terminal) {
+    if (!h) return fail("os2r_step_host_packed_end: null handle");
+    if (!h->packed_pending) return fail("os2r_step_host_packed_end: no packed step in flight");
+    DeviceGuard guard(h->device);
+    os2r_packed_layout L;
+    packed_layout(h, h->packed_prefix, &L);
+    h->packed_pending = false;
+    CK(cudaStreamSynchronize(h->host_stream));
+    if (!h->packed_block_pinned) memcpy(h->packed_block, h->pin_block, (size_t)L.total_bytes);
+    if (n_terminal) *n_terminal = *(const int32_t *)((const unsigned char *)h->packed_block + L.term_count);
+    return 0;
+}
+
+int32_t os2r_step_host_packed(os2r_env *h, const float *actions, void *block, int32_t prefix_records, int32_t *n_terminal) {
+    if (os2r_step_host_packed_begin(h, actions, block, prefix_records)) return 1;
+    return os2r_step_host_packed_end(h, n_terminal);
 }
 
 int32_t os2r_fetch_terminal_records(os2r_env *h, int32_t first, int32_t count, int32_t *records_host) {

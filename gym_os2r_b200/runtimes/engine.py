@@ -47,6 +47,8 @@ class Engine:
         self.terminal_obs = torch.zeros((N, D), dtype=torch.float32, **kw)
         self.info = torch.zeros((N, 2), dtype=torch.int32, **kw)
         self._host_pool = {}
+        self._packed_layouts = {}
+        self._packed_inflight = None
 
     # ------------------------------------------------------------------ lifecycle
     def close(self):
@@ -119,27 +121,37 @@ class Engine:
         _capi.check(self.lib.os2r_step_host(self.handle, p(a), p(obs), p(rew), p(done), p(term), p(info)), self.lib)
         return obs, rew, done, term, info
 
-    def step_host_packed(self, actions: np.ndarray, prefix_records: int = None):
-        """numpy in / numpy out at full batch size through ``os2r_step_host_packed``: ONE device-to-host copy into
-        one page-locked block; the returned arrays are views of that block (recycled only once the caller has dropped
-        every view). Returns ``(obs[N,D], reward[N], done[N] bool, reset_id[N] uint8, term_idx[k], term_cause[k],
-        term_obs[k,D])`` where the ``term_*`` arrays describe the k envs that finished an episode in this step."""
+    def step_host_packed_begin(self, actions: np.ndarray, prefix_records: int = None):
+        """First half of ``step_host_packed`` (``os2r_step_host_packed_begin``): stages the actions and enqueues
+        H2D + kernel + D2H, then returns without waiting — ``VecEnv.step_async``. ``actions`` may be reused at once."""
         a = np.ascontiguousarray(actions, dtype=np.float32)
         if a.shape != (self.n_envs, 2):
             raise ValueError(f'actions must have shape ({self.n_envs}, 2), got {a.shape}')
-        N, D = self.n_envs, self.obs_dim
+        N = self.n_envs
         if prefix_records is None:
             prefix_records = min(N, max(256, N // 64))
-        L = self._packed_layouts.get(prefix_records) if hasattr(self, '_packed_layouts') else None
+        L = self._packed_layouts.get(prefix_records)
         if L is None:
             L = _capi.PackedLayout()
             _capi.check(self.lib.os2r_packed_layout_get(self.handle, int(prefix_records), C.byref(L)), self.lib)
-            self.__dict__.setdefault('_packed_layouts', {})[prefix_records] = L
+            self._packed_layouts[prefix_records] = L
         block = self._host_array(('block', prefix_records), (int(L.total_bytes),), torch.uint8)
+        _capi.check(self.lib.os2r_step_host_packed_begin(self.handle, a.ctypes.data_as(C.c_void_p),
+                                                         block.ctypes.data_as(C.c_void_p), int(prefix_records)), self.lib)
+        self._packed_inflight = (block, L, int(prefix_records))
+
+    def step_host_packed_end(self):
+        """Second half (``os2r_step_host_packed_end``): waits for the step enqueued by ``step_host_packed_begin`` and
+        returns ``(obs[N,D], reward[N], done[N] bool, reset_id[N] uint8, term_idx[k], term_cause[k], term_obs[k,D])``,
+        views of ONE page-locked block (recycled only once the caller has dropped every view); the ``term_*`` arrays
+        describe the k envs that finished an episode in this step."""
+        if self._packed_inflight is None:
+            raise _capi.Os2rError('step_host_packed_end without a step in flight')
+        block, L, prefix_records = self._packed_inflight
+        self._packed_inflight = None
         n_term = C.c_int32(0)
-        _capi.check(self.lib.os2r_step_host_packed(self.handle, a.ctypes.data_as(C.c_void_p),
-                                                   block.ctypes.data_as(C.c_void_p), int(prefix_records),
-                                                   C.byref(n_term)), self.lib)
+        _capi.check(self.lib.os2r_step_host_packed_end(self.handle, C.byref(n_term)), self.lib)
+        N, D = self.n_envs, self.obs_dim
         obs = block[L.obs:L.obs + N * D * 4].view(np.float32).reshape(N, D)
         rew = block[L.reward:L.reward + N * 4].view(np.float32)
         done = block[L.done:L.done + N].view(np.bool_)
@@ -151,6 +163,11 @@ class Engine:
             rec = np.empty((k, rw), dtype=np.int32)
             _capi.check(self.lib.os2r_fetch_terminal_records(self.handle, 0, k, rec.ctypes.data_as(C.c_void_p)), self.lib)
         return obs, rew, done, rid, rec[:, 0], rec[:, 1], rec[:, 2:].view(np.float32)
+
+    def step_host_packed(self, actions: np.ndarray, prefix_records: int = None):
+        """numpy in / numpy out at full batch size: ONE device-to-host copy into one page-locked block."""
+        self.step_host_packed_begin(actions, prefix_records)
+        return self.step_host_packed_end()
 
     # ------------------------------------------------------------------ state access
     def get_state(self) -> np.ndarray:

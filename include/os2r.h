@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define OS2R_ABI_VERSION 6
+#define OS2R_ABI_VERSION 7
 
 #define OS2R_MAX_DOF 5
 #define OS2R_MAX_CONTACTS 4
@@ -211,6 +211,12 @@ int32_t os2r_packed_layout_get(const os2r_env *env, int32_t prefix_records, os2r
  * prefix_records the remaining records are fetched with os2r_fetch_terminal_records before the next step. */
 int32_t os2r_step_host_packed(os2r_env *env, const float *actions, void *block, int32_t prefix_records,
                               int32_t *n_terminal);
+/* The same step in two halves, for VecEnv.step_async / step_wait (subproc_vec_env.py:114-123: send the actions, do
+ * other work, collect): _begin stages the actions and enqueues H2D + kernel + D2H on the handle's stream and returns;
+ * _end waits and completes the block. `actions` may be reused after _begin returns; `block` must stay untouched
+ * until _end. One step in flight per handle. */
+int32_t os2r_step_host_packed_begin(os2r_env *env, const float *actions, void *block, int32_t prefix_records);
+int32_t os2r_step_host_packed_end(os2r_env *env, int32_t *n_terminal);
 int32_t os2r_fetch_terminal_records(os2r_env *env, int32_t first, int32_t count, int32_t *records_host);
 
 /* Packed double state [N, os2r_state_width] <-> device SoA (checkpoint/resume + parity tests). */

@@ -15,6 +15,7 @@ import pytest
 import torch
 
 import oracle
+from gym_os2r_b200 import _capi
 from gym_os2r_b200.runtimes.engine import Engine
 
 from helpers import chain_state, make_config
@@ -371,6 +372,16 @@ def test_packed_host_step_matches_device_step():
             finished += len(t_idx)
         assert finished == 2 * N and len(set(rid.tolist())) == 3
         assert np.array_equal(e1.get_state(), e2.get_state())
+        # the two halves behind VecEnv.step_async / step_wait: actions may be overwritten once _begin has returned
+        a = rng.uniform(-1, 1, (N, 2)).astype(np.float32)
+        o1 = e1.step(torch.as_tensor(a, device='cuda'))[0].cpu().numpy()
+        e2.step_host_packed_begin(a, prefix_records=prefix)
+        with pytest.raises(_capi.Os2rError, match='not been completed'):
+            e2.step_host_packed_begin(a, prefix_records=prefix)
+        a[:] = 0.0
+        np.testing.assert_array_equal(e2.step_host_packed_end()[0], o1)
+        with pytest.raises(_capi.Os2rError):
+            e2.step_host_packed_end()
         e1.close(); e2.close()
 
 

@@ -20,6 +20,13 @@ def t(fn, n=200):
     return (time.perf_counter() - t0) / n * 1e6
 print('VecEnv.step(numpy)            us:', t(lambda i: envs.step(acts[i % 8])))
 print('engine.step_host_packed        us:', t(lambda i: eng.step_host_packed(acts[i % 8])))
+import ctypes as C
+_blk = torch.empty(4 * 1024 * 1024, dtype=torch.uint8).pin_memory().numpy(); _k = C.c_int32()
+def one_call(i):
+    a = acts[i % 8]
+    eng.lib.os2r_step_host_packed(eng.handle, a.ctypes.data_as(C.c_void_p), _blk.ctypes.data_as(C.c_void_p), 1024, C.byref(_k))
+print('C os2r_step_host_packed (one call) us:', t(one_call))
+print('engine.step_host_packed again  us:', t(lambda i: eng.step_host_packed(acts[i % 8])))
 if os.environ.get('E2E_SHORT'):
     sys.exit(0)
 print('engine.step_host (obs,rew,done) us:', t(lambda i: eng.step_host(acts[i % 8])))
