@@ -1,5 +1,14 @@
 #!/usr/bin/env python
-"""A/B of the lane sort, block width, sort margin and sweep tolerance (kernel-only CUDA-event timings)."""
+"""Kernel A/B probe (kernel-only CUDA-event timings, hot L2, fresh random actions from a long pool).
+
+    python tools/exp_sort.py <mode>        # results are appended to gpurun_out/exp_sort.log
+      a  block width / sort margin / sweep tolerance sweep      d  sort-margin sweep at the production tolerance
+      b  batch sizes and the other task modes                   e  steady state, from-reset average, sort off
+      c  one library (OS2R_LIB=...) on the standard cases       g  strictly contact-free window (steps 5..60)
+      h  BASELINE config 4 (free_hip) and the small models
+Environment knobs read by libos2r.so at os2r_create: OS2R_FORCE_BLOCK=64|224, OS2R_SORT_MARGIN=<m> (-1 = sort off).
+A variant library built with other -D flags is selected with OS2R_LIB=/path/to/lib.so (see DESIGN.md section 9 for
+the experiments this was used for)."""
 import os, sys
 import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
