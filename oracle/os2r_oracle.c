@@ -306,32 +306,17 @@ void oracle_sweep_histogram(long long out[65], int clear) {
     for (int i = 0; i < 65; ++i) { out[i] = __atomic_load_n(&g_sweep_hist[i], __ATOMIC_RELAXED); if (clear) __atomic_store_n(&g_sweep_hist[i], 0, __ATOMIC_RELAXED); }
 }
 
-/* M = Minv^-1 by Gauss-Jordan (n <= 5, SPD): only the convergence measure needs it. */
-static void invert_spd(int n, double A[NMAX][NMAX], double B[NMAX][NMAX]) {
-    double W[NMAX][2 * NMAX];
-    for (int i = 0; i < n; ++i) for (int j = 0; j < n; ++j) { W[i][j] = A[i][j]; W[i][n + j] = i == j; }
-    for (int c = 0; c < n; ++c) {
-        int p = c;
-        for (int r = c + 1; r < n; ++r) if (fabs(W[r][c]) > fabs(W[p][c])) p = r;
-        if (p != c) for (int j = 0; j < 2 * n; ++j) { double t = W[c][j]; W[c][j] = W[p][j]; W[p][j] = t; }
-        double d = 1.0 / W[c][c];
-        for (int j = 0; j < 2 * n; ++j) W[c][j] *= d;
-        for (int r = 0; r < n; ++r) if (r != c) { double f = W[r][c]; for (int j = 0; j < 2 * n; ++j) W[r][j] -= f * W[c][j]; }
-    }
-    for (int i = 0; i < n; ++i) for (int j = 0; j < n; ++j) B[i][j] = W[i][n + j];
-}
-
 /* Projected Gauss-Seidel, fixed row order, at most `sweeps` sweeps. The iteration of this env ends after
  * the first sweep whose velocity change is <= tol in the kinetic-energy norm sqrt(dv^T M dv) (the kernel
  * measures the same quantity as |dz| in its Cholesky-whitened coordinates); tol = 0 ends it only when a
- * sweep left the velocity exactly unchanged (os2r_model.pgs_tol, include/os2r.h). */
+ * sweep left the velocity exactly unchanged (os2r_model.pgs_tol, include/os2r.h). The norm needs no mass
+ * matrix: dv = Minv J^T dlam, so dv^T M dv = sum_r dlam_r (J_r . dv). */
 static void pgs_sweeps(const os2r_model *M, const env_params *P, const constraint_set *S,
                        double Minv[NMAX][NMAX], double *v, double *lam, int sweeps, double tol) {
     int n = M->n_dof, it;
-    double Mass[NMAX][NMAX];
-    invert_spd(n, Minv, Mass);
+    (void)Minv;
     for (it = 0; it < sweeps; ) {
-        double v0[NMAX];
+        double v0[NMAX], dlam[RMAX] = {0};
         for (int i = 0; i < n; ++i) v0[i] = v[i];
         for (int r = 0; r < S->n_rows; ++r) {
             if (!S->active[r]) continue;
@@ -350,10 +335,16 @@ static void pgs_sweeps(const os2r_model *M, const env_params *P, const constrain
             double dl = nl - lam[r];
             for (int i = 0; i < n; ++i) v[i] += S->MiJt[r][i] * dl;
             lam[r] = nl;
+            dlam[r] = dl;
         }
         ++it;
         double e2 = 0;
-        for (int i = 0; i < n; ++i) for (int j = 0; j < n; ++j) e2 += (v[i] - v0[i]) * Mass[i][j] * (v[j] - v0[j]);
+        for (int r = 0; r < S->n_rows; ++r) {
+            if (dlam[r] == 0.0) continue;
+            double jdv = 0;
+            for (int i = 0; i < n; ++i) jdv += S->J[r][i] * (v[i] - v0[i]);
+            e2 += dlam[r] * jdv;
+        }
         if (e2 <= tol * tol) break;
     }
     __atomic_fetch_add(&g_sweep_hist[it < 64 ? it : 64], 1, __ATOMIC_RELAXED);
