@@ -126,6 +126,8 @@ __device__ __forceinline__ float rcp_t(float x) {
     return r;
 }
 __device__ __forceinline__ double rcp_t(double x) { return 1.0 / x; }
+__device__ __forceinline__ float fma_t(float a, float b, float c) { return fmaf(a, b, c); }
+__device__ __forceinline__ double fma_t(double a, double b, double c) { return fma(a, b, c); }
 __device__ __forceinline__ float fmin_t(float a, float b) { return fminf(a, b); }
 __device__ __forceinline__ double fmin_t(double a, double b) { return fmin(a, b); }
 __device__ __forceinline__ float fmax_t(float a, float b) { return fmaxf(a, b); }
@@ -180,11 +182,20 @@ template <> __device__ __forceinline__ int __float_as_int_t<double>(double v) { 
         (o)[1] = (a)[2] * (b)[0] - (a)[0] * (b)[2]; \
         (o)[2] = (a)[0] * (b)[1] - (a)[1] * (b)[0]; \
     } while (0)
-#define OS2R_CROSS_ACC(o, a, b)                 \
-    do {                                        \
-        (o)[0] += (a)[1] * (b)[2] - (a)[2] * (b)[1]; \
-        (o)[1] += (a)[2] * (b)[0] - (a)[0] * (b)[2]; \
-        (o)[2] += (a)[0] * (b)[1] - (a)[1] * (b)[0]; \
+// o += a x b, accumulated term by term: two FMAs per component. Written as o += (a1*b2 - a2*b1) the compiler has to
+// respect the parentheses (FMUL + FFMA + FADD); the forward pass is issue-bound, so the saved instruction counts.
+#define OS2R_CROSS_ACC(o, a, b)                                               \
+    do {                                                                      \
+        (o)[0] = fma_t((a)[1], (b)[2], (o)[0]); (o)[0] = fma_t(-(a)[2], (b)[1], (o)[0]); \
+        (o)[1] = fma_t((a)[2], (b)[0], (o)[1]); (o)[1] = fma_t(-(a)[0], (b)[2], (o)[1]); \
+        (o)[2] = fma_t((a)[0], (b)[1], (o)[2]); (o)[2] = fma_t(-(a)[1], (b)[0], (o)[2]); \
+    } while (0)
+// acc += a . b as a chain of three FMAs (instead of FMUL + 2 FFMA + FADD)
+#define OS2R_DOT_ACC(acc, a, b)                   \
+    do {                                          \
+        (acc) = fma_t((a)[0], (b)[0], (acc));     \
+        (acc) = fma_t((a)[1], (b)[1], (acc));     \
+        (acc) = fma_t((a)[2], (b)[2], (acc));     \
     } while (0)
 #define OS2R_DOT(a, b) ((a)[0] * (b)[0] + (a)[1] * (b)[1] + (a)[2] * (b)[2])
 
@@ -404,9 +415,13 @@ __device__ __forceinline__ void physics_iteration(const ModelDev<T> &M, EnvRegs<
                 const T rr[3] = {p[0] + d[0] - P[j][0], p[1] + d[1] - P[j][1], p[2] + d[2] - P[j][2]};
                 OS2R_CROSS(Jv[j], ax[j], rr);
                 OS2R_SYMV(u[j], Iw, ax[j]);
-                hb[j] += OS2R_DOT(Jv[j], f) + OS2R_DOT(ax[j], nn);
+                OS2R_DOT_ACC(hb[j], Jv[j], f);
+                OS2R_DOT_ACC(hb[j], ax[j], nn);
 #pragma unroll
-                for (int k = 0; k <= j; ++k) Mm[j][k] += m * OS2R_DOT(Jv[j], Jv[k]) + OS2R_DOT(ax[j], u[k]);
+                for (int k = 0; k <= j; ++k) {
+                    Mm[j][k] = fma_t(m, OS2R_DOT(Jv[j], Jv[k]), Mm[j][k]);
+                    OS2R_DOT_ACC(Mm[j][k], ax[j], u[k]);
+                }
             }
             // contact spheres carried by this body
 #pragma unroll
