@@ -109,6 +109,22 @@ void build_model_dev(const os2r_model &m, ModelDev<T> &d) {
     // lane-sorting hint: a proxy within this clearance may touch down during the next env step
     const char *margin = getenv("OS2R_SORT_MARGIN");
     d.sort_margin = (T)(margin ? atof(margin) : 0.002);
+    // Root body turning about an axis parallel to gravity (z): its contribution to the joint-space dynamics is the
+    // constant inertia about that axis (see ModelDev::root_spin). Axis of joint 0 in the world = first column of the
+    // normalised tree_R[0]; the tilt tolerance (1e-9 rad) is far below the fp32 kernel's own rounding
+    // (the URDF's "3.14159265359" already tilts the yaw axis by 2e-13 rad).
+    {
+        double a[3] = {(double)d.tree_R[0][0], (double)d.tree_R[0][3], (double)d.tree_R[0][6]};
+        const bool vertical = fabs(a[0]) < 1e-9 && fabs(a[1]) < 1e-9 && fabs(fabs(a[2]) - 1.0) < 1e-9;
+        bool carries_contact = false;
+        for (int c = 0; c < m.n_contacts; ++c) carries_contact = carries_contact || m.contact_body[c] == 0;
+        d.root_spin = (vertical && !getenv("OS2R_NO_ROOT_SPIN")) ? 1 : 0;
+        (void)carries_contact;   // the proxies' positions are still computed from body 0's frame
+        // |a x com|^2 with a = e_x in the normalised body frame: com_y^2 + com_z^2 ; a.I.a = Ixx
+        const double cy = (double)d.com[0][1], cz = (double)d.com[0][2];
+        d.root_mass_term = (T)(m.mass[0] * (cy * cy + cz * cz));
+        d.root_inertia_term = (T)(double)d.inertia[0][0];
+    }
     d.any_damping = 0;
     for (int i = 0; i < m.n_dof; ++i) if (m.damping[i] != 0.0) d.any_damping = 1;
 }

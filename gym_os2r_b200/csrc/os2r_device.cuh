@@ -46,6 +46,7 @@ struct ModelDev {
     T dt, erp_over_dt, max_erv, cfm_contact, cfm_joint;
     T cfm1_contact, cfm1_joint;  // 1 + cfm
     T kc1, kj1;                  // 1 / (1 + cfm)  (host-side: an IEEE division per physics iteration otherwise)
+    T root_mass_term, root_inertia_term;  // see root_spin below
     T pgs_tol2;                  // squared energy-norm tolerance of the sweeps (os2r_model.pgs_tol)
     T sort_margin;               // ground clearance below which a contact proxy counts as "near" (lane sorting hint)
     T max_torque[2];
@@ -53,6 +54,10 @@ struct ModelDev {
     int32_t hip_dof, knee_dof;
     int32_t substeps, pgs_iters;
     int32_t any_damping;         // 0 when every joint's nominal damping is 0 (skip 2nd factorisation)
+    int32_t root_spin;           // 1: body 0 hangs off the world and turns about an axis parallel to gravity (the yaw
+                                 //    pivot). Its whole contribution to the dynamics is then a CONSTANT added to M[0][0]
+                                 //    (mass * |a x d|^2 * mass_scale + a.I.a: rotation about a leaves both unchanged) and
+                                 //    nothing to the bias (gravity || a, centrifugal force radial): the host folds it.
 };
 
 struct TaskDev {                 // epilogue + reset configuration (fp64: evaluated once per env step)
@@ -373,6 +378,9 @@ __device__ __forceinline__ void physics_iteration(const ModelDev<T> &M, EnvRegs<
             }
 #pragma unroll
             for (int r = 0; r < 3; ++r) w[r] += ax[i][r] * qd;
+            if (i == 0 && M.root_spin) {   // warp-uniform; ~130 instructions of body 0 become one FMA
+                Mm[0][0] = fma_t(M.root_mass_term, C(SL::MASS), M.root_inertia_term);
+            } else {
             // COM offset and rotational inertia in world axes
             const T *cm = M.com[i];
             T d[3];
@@ -422,6 +430,7 @@ __device__ __forceinline__ void physics_iteration(const ModelDev<T> &M, EnvRegs<
                     Mm[j][k] = fma_t(m, OS2R_DOT(Jv[j], Jv[k]), Mm[j][k]);
                     OS2R_DOT_ACC(Mm[j][k], ax[j], u[k]);
                 }
+            }
             }
             // contact spheres carried by this body
 #pragma unroll

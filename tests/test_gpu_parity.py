@@ -118,6 +118,36 @@ def test_damping_written_through_set_params_is_implicit():
         eng.close()
 
 
+def test_root_spin_shortcut_matches_general_path(monkeypatch):
+    """The yaw pivot (root body turning about an axis parallel to gravity) is folded on the host into a constant added
+    to M[0][0] (os2r_device.cuh: ModelDev::root_spin). With the fold disabled the kernel runs the general per-body code
+    for it; both must agree to fp64 rounding (the only neglected terms come from the URDF's 2e-13 rad tilt of the axis)."""
+    N = 512
+    rng = np.random.RandomState(31)
+    for mode in ('fixed_hip', 'free_hip'):
+        task, cm, cfg = make_config(mode, reward='BalancingV1' if mode == 'fixed_hip' else 'HoppingV1',
+                                    randomize_params=True, reset_randomized=True)
+        st = _random_state(cm, N, rng, True)
+        a = rng.uniform(-1, 1, (N, 2)).astype(np.float32)
+        out = []
+        for disable in (False, True):
+            if disable:
+                monkeypatch.setenv('OS2R_NO_ROOT_SPIN', '1')
+            else:
+                monkeypatch.delenv('OS2R_NO_ROOT_SPIN', raising=False)
+            eng = Engine(cm, cfg, N, seed=3, precision=64)
+            eng.reset()                                  # draws the per-env mass scales (the fold uses body 0's)
+            eng.set_state(st)
+            for _ in range(3):
+                eng.step(torch.as_tensor(a, device='cuda'))
+            out.append(eng.get_state())
+            eng.close()
+        n = cm.n_dof
+        assert np.abs(out[0][:, :n] - out[1][:, :n]).max() < 1e-10, mode
+        assert np.abs(out[0][:, n:2 * n] - out[1][:, n:2 * n]).max() < 1e-8, mode
+    monkeypatch.delenv('OS2R_NO_ROOT_SPIN', raising=False)
+
+
 def test_contact_free_trajectory_simple():
     """BASELINE config 2a: `simple` mode (2 DoF, never touches the ground), sinusoidal actions A = 0.1,
     f = (1.0, 1.7) Hz, random phases, 1000 env steps: fp32 kernel within 1e-4 rad / 1e-3 rad/s of the oracle."""
