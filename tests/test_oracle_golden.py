@@ -103,3 +103,27 @@ def test_reward_support_lists():
     assert r.get_supported_task_modes() == ['simple'] and not r.is_task_supported('fixed_hip')
     assert rewards.BalancingV1({}, True).is_task_supported('free_hip')
     assert not rewards.HoppingV1({}, True).is_task_supported('simple')
+
+
+def test_oracle_physics_regression_fixture():
+    """The oracle's physics is pinned against ITSELF (tools/gen_oracle_regression.py): a regression guard for the
+    restatement — touchdown, sliding contact, joint friction, implicit damping, both sweep-exit modes — not a parity
+    claim (the reference holds no trajectory to pin it to)."""
+    import json
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'tools'))
+    import gen_oracle_regression as gen
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'oracle_physics_regression.json')
+    data = json.load(open(path))
+    touched = 0
+    for case in data['cases']:
+        got = gen.trajectory(case['mode'], case['reward'], case['reset'], case['pgs_tol'])
+        for step, snap in case['snapshots'].items():
+            np.testing.assert_allclose(got[step]['state'], snap['state'], rtol=0, atol=1e-10, err_msg=f"{case['mode']} {case['reset']} tol={case['pgs_tol']} step {step}")
+            np.testing.assert_allclose(got[step]['obs'], snap['obs'], rtol=0, atol=1e-10)
+            assert got[step]['reward'] == snap['reward']
+        n = {'simple': 2, 'fixed': 3, 'fixed_hip': 4, 'free_hip': 5}[case['mode']]
+        for snap in case['snapshots'].values():
+            touched += int((np.array(snap['state'])[3 * n:3 * n + 9:3] > 0).any())
+    assert touched >= 4      # several snapshots catch a proxy pressing on the ground (the others are between bounces)
