@@ -154,6 +154,7 @@ struct os2r_env {
     StatsDev *stats = nullptr;
     int sm_count = 0;
     int block = OS2R_BLOCK;          // threads per block of the step kernel for this batch size
+    bool lone = false;               // at most one 2-warp block per SM: the build without an occupancy target
     StateDev<float> s32;
     StateDev<double> s64;
     // host staging for os2r_step_host
@@ -312,9 +313,9 @@ int set_params_impl(os2r_env *h, StateDev<T> &S, const double *in) {
 int do_step(os2r_env *h, const StepIO &io, cudaStream_t stream) {
     cudaError_t e;
     if (h->precision == 32)
-        e = launch_step<float>(h->model.n_dof, h->model.n_contacts, h->block, h->m32, h->taskdev, h->s32, io, h->stats, stream);
+        e = launch_step<float>(h->model.n_dof, h->model.n_contacts, h->block, h->lone, h->m32, h->taskdev, h->s32, io, h->stats, stream);
     else
-        e = launch_step<double>(h->model.n_dof, h->model.n_contacts, h->block, h->m64, h->taskdev, h->s64, io, h->stats, stream);
+        e = launch_step<double>(h->model.n_dof, h->model.n_contacts, h->block, false, h->m64, h->taskdev, h->s64, io, h->stats, stream);
     if (e != cudaSuccess) return fail("step kernel launch failed: %s", cudaGetErrorString(e));
     h->launches += 1;
     h->env_steps += (uint64_t)h->n;
@@ -362,6 +363,9 @@ int32_t os2r_create(const os2r_model *model, const os2r_task_cfg *task, int64_t 
     const char *force_block = getenv("OS2R_FORCE_BLOCK");   // experiments only
     h->block = precision == 32 ? step_block_threads<float>(n_envs, sm_count) : step_block_threads<double>(n_envs, sm_count);
     if (force_block && (atoi(force_block) == OS2R_BLOCK || (precision == 32 && atoi(force_block) == OS2R_BLOCK_WIDE))) h->block = atoi(force_block);
+    h->lone = precision == 32 && h->block == OS2R_BLOCK && n_envs <= (int64_t)sm_count * OS2R_BLOCK;
+    const char *force_lone = getenv("OS2R_FORCE_LONE");   // experiments: 0 or 1
+    if (force_lone && precision == 32 && h->block == OS2R_BLOCK) h->lone = atoi(force_lone) != 0;
     h->model = *model; h->task = *task; h->precision = precision; h->device = device;
     h->n = n_envs; h->first_env_id = first_env_id; h->seed = seed;
     h->rows = model->n_dof + 3 * model->n_contacts;

@@ -130,12 +130,10 @@ __device__ __forceinline__ int sorted_source(int key, int *scratch) {
 // ------------------------------------------------------------------------------------------------
 // the fused step kernel: substeps x physics + observation + reward + done + auto-reset
 // ------------------------------------------------------------------------------------------------
-template <typename T, int N, int NC, int BLOCK, bool DAMPED>
-#ifdef OS2R_MAXNREG
-__global__ void __maxnreg__(sizeof(T) == 4 ? OS2R_MAXNREG : 255)
-#else
-__global__ void __launch_bounds__(BLOCK, (sizeof(T) == 4 ? OS2R_RESIDENT_THREADS / BLOCK : 1))
-#endif
+// LONE = the build for batches of at most one 2-warp block per SM: no occupancy target, so ptxas may use up to 255
+// registers and schedule for instruction-level parallelism (a lone warp is bound by its dependency chains).
+template <typename T, int N, int NC, int BLOCK, bool DAMPED, bool LONE>
+__global__ void __launch_bounds__(BLOCK, (sizeof(T) == 4 && !LONE ? OS2R_RESIDENT_THREADS / BLOCK : 1))
 step_kernel(const __grid_constant__ ModelDev<T> M, const __grid_constant__ TaskDev K, StateDev<T> S,
             const __grid_constant__ StepIO IO, StatsDev *stats) {
     const float *__restrict__ actions = IO.actions;
@@ -364,39 +362,45 @@ int step_block_threads(int64_t n_envs, int sm_count) {
 
 template <typename T, int N, int BLOCK, bool DAMPED>
 static cudaError_t launch_step_nd(const ModelDev<T> &M, const TaskDev &K, const StateDev<T> &S, const StepIO &io, StatsDev *stats,
-                                  cudaStream_t stream) {
+                                  cudaStream_t stream, bool lone) {
     constexpr size_t smem = step_smem_bytes<T, N, BLOCK>();
+    if constexpr (sizeof(T) == 4 && BLOCK == OS2R_BLOCK) {
+        if (lone) {
+            step_kernel<T, N, OS2R_NC, BLOCK, DAMPED, true><<<grid_for(S.n_envs, BLOCK), BLOCK, smem, stream>>>(M, K, S, io, stats);
+            return cudaGetLastError();
+        }
+    }
     if (smem > 48 * 1024) {
         static bool raised = false;   // per kernel instantiation
         if (!raised) {
-            cudaError_t e = cudaFuncSetAttribute(step_kernel<T, N, OS2R_NC, BLOCK, DAMPED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            cudaError_t e = cudaFuncSetAttribute(step_kernel<T, N, OS2R_NC, BLOCK, DAMPED, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return e;
             raised = true;
         }
     }
-    step_kernel<T, N, OS2R_NC, BLOCK, DAMPED><<<grid_for(S.n_envs, BLOCK), BLOCK, smem, stream>>>(M, K, S, io, stats);
+    step_kernel<T, N, OS2R_NC, BLOCK, DAMPED, false><<<grid_for(S.n_envs, BLOCK), BLOCK, smem, stream>>>(M, K, S, io, stats);
     return cudaGetLastError();
 }
 template <typename T, int N, int BLOCK>
 static cudaError_t launch_step_n(const ModelDev<T> &M, const TaskDev &K, const StateDev<T> &S, const StepIO &io, StatsDev *stats,
-                                 cudaStream_t stream) {
+                                 cudaStream_t stream, bool lone) {
     // the fp64 verification build keeps one (damped) instantiation; with zero damping its second factor equals the first
-    if (sizeof(T) == 8 || M.any_damping) return launch_step_nd<T, N, BLOCK, true>(M, K, S, io, stats, stream);
-    if constexpr (sizeof(T) == 4) return launch_step_nd<T, N, BLOCK, false>(M, K, S, io, stats, stream);
+    if (sizeof(T) == 8 || M.any_damping) return launch_step_nd<T, N, BLOCK, true>(M, K, S, io, stats, stream, lone);
+    if constexpr (sizeof(T) == 4) return launch_step_nd<T, N, BLOCK, false>(M, K, S, io, stats, stream, lone);
     return cudaErrorInvalidValue;
 }
 
 template <typename T>
-cudaError_t launch_step(int n_dof, int n_contacts, int block, const ModelDev<T> &M, const TaskDev &K, const StateDev<T> &S,
-                        const StepIO &io, StatsDev *stats, cudaStream_t stream) {
+cudaError_t launch_step(int n_dof, int n_contacts, int block, bool lone, const ModelDev<T> &M, const TaskDev &K,
+                        const StateDev<T> &S, const StepIO &io, StatsDev *stats, cudaStream_t stream) {
     if (n_contacts != OS2R_NC) return cudaErrorInvalidValue;
     if (sizeof(T) == 4 && block == OS2R_BLOCK_WIDE) {
         if constexpr (sizeof(T) == 4) {
-            OS2R_DISPATCH_N(n_dof, return (launch_step_n<T, N_, OS2R_BLOCK_WIDE>(M, K, S, io, stats, stream)));
+            OS2R_DISPATCH_N(n_dof, return (launch_step_n<T, N_, OS2R_BLOCK_WIDE>(M, K, S, io, stats, stream, false)));
         }
     }
     if (block != OS2R_BLOCK) return cudaErrorInvalidValue;
-    OS2R_DISPATCH_N(n_dof, return (launch_step_n<T, N_, OS2R_BLOCK>(M, K, S, io, stats, stream)));
+    OS2R_DISPATCH_N(n_dof, return (launch_step_n<T, N_, OS2R_BLOCK>(M, K, S, io, stats, stream, lone)));
     return cudaErrorInvalidValue;
 }
 
@@ -417,13 +421,13 @@ cudaError_t launch_init(const TaskDev &K, const StateDev<T> &S, double nominal_g
 template <typename T, int N, int BLOCK, bool DAMPED>
 static cudaError_t step_attr_nd(cudaFuncAttributes *attr, int *blocks_per_sm) {
     constexpr size_t smem = step_smem_bytes<T, N, BLOCK>();
-    cudaError_t e = cudaFuncGetAttributes(attr, step_kernel<T, N, OS2R_NC, BLOCK, DAMPED>);
+    cudaError_t e = cudaFuncGetAttributes(attr, step_kernel<T, N, OS2R_NC, BLOCK, DAMPED, false>);
     if (e != cudaSuccess) return e;
     if (smem > 48 * 1024) {
-        e = cudaFuncSetAttribute(step_kernel<T, N, OS2R_NC, BLOCK, DAMPED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        e = cudaFuncSetAttribute(step_kernel<T, N, OS2R_NC, BLOCK, DAMPED, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, step_kernel<T, N, OS2R_NC, BLOCK, DAMPED>, BLOCK, smem);
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, step_kernel<T, N, OS2R_NC, BLOCK, DAMPED, false>, BLOCK, smem);
 }
 template <typename T, int N, int BLOCK>
 static cudaError_t step_attr_n(bool damped, cudaFuncAttributes *attr, int *blocks_per_sm) {
@@ -450,7 +454,7 @@ cudaError_t launch_fma_peak(float *out, int blocks, int iters, cudaStream_t stre
 
 #define OS2R_INSTANTIATE(T)                                                                                   \
     template int step_block_threads<T>(int64_t, int);                                                         \
-    template cudaError_t launch_step<T>(int, int, int, const ModelDev<T> &, const TaskDev &, const StateDev<T> &, \
+    template cudaError_t launch_step<T>(int, int, int, bool, const ModelDev<T> &, const TaskDev &, const StateDev<T> &, \
                                         const StepIO &, StatsDev *, cudaStream_t);                            \
     template cudaError_t launch_reset<T>(int, int, const TaskDev &, const StateDev<T> &, const uint8_t *,     \
                                          float *, cudaStream_t);                                              \

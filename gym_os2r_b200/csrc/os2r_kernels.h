@@ -22,8 +22,8 @@ namespace os2r {
 template <typename T>
 int step_block_threads(int64_t n_envs, int sm_count);
 template <typename T>
-cudaError_t launch_step(int n_dof, int n_contacts, int block, const ModelDev<T> &M, const TaskDev &K, const StateDev<T> &S,
-                        const StepIO &io, StatsDev *stats, cudaStream_t stream);
+cudaError_t launch_step(int n_dof, int n_contacts, int block, bool lone, const ModelDev<T> &M, const TaskDev &K,
+                        const StateDev<T> &S, const StepIO &io, StatsDev *stats, cudaStream_t stream);
 template <typename T>
 cudaError_t launch_reset(int n_dof, int n_contacts, const TaskDev &K, const StateDev<T> &S, const uint8_t *mask,
                          float *obs, cudaStream_t stream);

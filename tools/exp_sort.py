@@ -5,7 +5,7 @@
       a  block width / sort margin / sweep tolerance sweep      d  sort-margin sweep at the production tolerance
       b  batch sizes and the other task modes                   e  steady state, from-reset average, sort off
       c  one library (OS2R_LIB=...) on the standard cases       g  strictly contact-free window (steps 5..60)
-      h  BASELINE config 4 (free_hip) and the small models
+      h  BASELINE config 4 (free_hip) and the small models      l  small batches: OS2R_FORCE_LONE=0|1
 Environment knobs read by libos2r.so at os2r_create: OS2R_FORCE_BLOCK=64|224, OS2R_SORT_MARGIN=<m> (-1 = sort off).
 A variant library built with other -D flags is selected with OS2R_LIB=/path/to/lib.so (see DESIGN.md section 9 for
 the experiments this was used for)."""
@@ -112,6 +112,14 @@ if __name__ == '__main__':
         P(run(mode='free_hip', iters=8, tol=1e-6)); P(run(mode='free_hip', iters=8, tol=1e-6, N=131072, pre=800))
         P(run(mode='free_hip', iters=8, tol=1e-6, pre=0))
         P(run(mode='fixed', iters=8, tol=1e-6, pre=1000)); P(run(mode='simple', iters=8, tol=1e-6, pre=100))
+    if which == 'l':     # small batches: build without an occupancy target (LONE) vs the 128-register build
+        for N in (32, 1024, 4736, 9472):
+            for lone in (0, 1):
+                P(run(N=N, iters=8, tol=1e-6, pre=1500, steps=300, env={'OS2R_FORCE_LONE': lone}))
+                P(run(N=N, iters=8, tol=1e-6, pre=0, steps=60, env={'OS2R_FORCE_LONE': lone}))
+        for mode in ('free_hip', 'simple'):
+            for lone in (0, 1):
+                P(run(mode=mode, N=1024, iters=8, tol=1e-6, pre=300, steps=300, env={'OS2R_FORCE_LONE': lone}))
     if which in ('all', 'b'):
         for N in (9472, 16384, 33152, 131072):
             P(run(N=N)); P(run(N=N, env={'OS2R_FORCE_BLOCK': 64}))
