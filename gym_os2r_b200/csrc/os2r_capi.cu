@@ -154,7 +154,7 @@ struct os2r_env {
     StatsDev *stats = nullptr;
     int sm_count = 0;
     int block = OS2R_BLOCK;          // threads per block of the step kernel for this batch size
-    bool lone = false;               // at most one 2-warp block per SM: the build without an occupancy target
+    bool lone = false;               // at most four 2-warp blocks per SM: the build without an occupancy target
     StateDev<float> s32;
     StateDev<double> s64;
     // host staging for os2r_step_host
@@ -363,7 +363,8 @@ int32_t os2r_create(const os2r_model *model, const os2r_task_cfg *task, int64_t 
     const char *force_block = getenv("OS2R_FORCE_BLOCK");   // experiments only
     h->block = precision == 32 ? step_block_threads<float>(n_envs, sm_count) : step_block_threads<double>(n_envs, sm_count);
     if (force_block && (atoi(force_block) == OS2R_BLOCK || (precision == 32 && atoi(force_block) == OS2R_BLOCK_WIDE))) h->block = atoi(force_block);
-    h->lone = precision == 32 && h->block == OS2R_BLOCK && n_envs <= (int64_t)sm_count * OS2R_BLOCK;
+    // up to four 2-warp blocks per SM fit at ~225 registers per thread: every batch that runs on the narrow blocks
+    h->lone = precision == 32 && h->block == OS2R_BLOCK && n_envs <= (int64_t)sm_count * 4 * OS2R_BLOCK;
     const char *force_lone = getenv("OS2R_FORCE_LONE");   // experiments: 0 or 1
     if (force_lone && precision == 32 && h->block == OS2R_BLOCK) h->lone = atoi(force_lone) != 0;
     h->model = *model; h->task = *task; h->precision = precision; h->device = device;

@@ -130,8 +130,9 @@ __device__ __forceinline__ int sorted_source(int key, int *scratch) {
 // ------------------------------------------------------------------------------------------------
 // the fused step kernel: substeps x physics + observation + reward + done + auto-reset
 // ------------------------------------------------------------------------------------------------
-// LONE = the build for batches of at most one 2-warp block per SM: no occupancy target, so ptxas may use up to 255
-// registers and schedule for instruction-level parallelism (a lone warp is bound by its dependency chains).
+// LONE = the build for batches of at most four 2-warp blocks per SM (every batch below the wide-block threshold): no
+// occupancy target, so ptxas takes ~200-225 registers instead of 128 and schedules for instruction-level parallelism
+// (with one or two warps per scheduler a warp is bound by its own dependency chains): 4-12 % lower step latency.
 template <typename T, int N, int NC, int BLOCK, bool DAMPED, bool LONE>
 __global__ void __launch_bounds__(BLOCK, (sizeof(T) == 4 && !LONE ? OS2R_RESIDENT_THREADS / BLOCK : 1))
 step_kernel(const __grid_constant__ ModelDev<T> M, const __grid_constant__ TaskDev K, StateDev<T> S,

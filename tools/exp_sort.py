@@ -120,6 +120,11 @@ if __name__ == '__main__':
         for mode in ('free_hip', 'simple'):
             for lone in (0, 1):
                 P(run(mode=mode, N=1024, iters=8, tol=1e-6, pre=300, steps=300, env={'OS2R_FORCE_LONE': lone}))
+    if which == 'm':     # mid-size batches (2..4 narrow blocks per SM): does the many-register build still win?
+        for N in (16384, 24576, 32768):
+            for lone in (0, 1):
+                P(run(N=N, iters=8, tol=1e-6, pre=1500, steps=300, env={'OS2R_FORCE_LONE': lone, 'OS2R_FORCE_BLOCK': 64}))
+        P(run(N=32768, iters=8, tol=1e-6, pre=1500, steps=300, env={'OS2R_FORCE_BLOCK': 224}))
     if which in ('all', 'b'):
         for N in (9472, 16384, 33152, 131072):
             P(run(N=N)); P(run(N=N, env={'OS2R_FORCE_BLOCK': 64}))
