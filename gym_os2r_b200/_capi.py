@@ -8,12 +8,12 @@ import ctypes as C
 import os
 
 MAX_DOF = 5
-MAX_CONTACTS = 4
+MAX_CONTACTS = 6
 MAX_OBS = 12
 MAX_RESETS = 8
 MAX_ROWS = MAX_DOF + 3 * MAX_CONTACTS
 N_ROLES = 5
-ABI_VERSION = 7
+ABI_VERSION = 8
 
 ROLE_HIP, ROLE_KNEE, ROLE_PITCH, ROLE_YAW, ROLE_BOOM_CONNECTOR = range(5)
 ROLE_OF_JOINT = {
@@ -54,6 +54,7 @@ class TaskCfg(C.Structure):
         ('obs_dim', _i32), ('normalized', _i32), ('reward_id', _i32), ('max_episode_steps', _i32),
         ('auto_reset', _i32), ('n_resets', _i32), ('reset_randomized', _i32),
         ('randomize_params', _i32), ('randomize_gravity', _i32), ('simple_sample_reset', _i32),
+        ('gravity_redraw_resets', _i32), ('_pad1', _i32),
         ('reward_pitch_col', _i32), ('reward_yawvel_col', _i32), ('reward_hip_col', _i32),
         ('reward_knee_col', _i32),
         ('obs_kind', _i32 * MAX_OBS), ('obs_index', _i32 * MAX_OBS),
@@ -68,6 +69,12 @@ class TaskCfg(C.Structure):
         ('damp_lo', _f64), ('damp_hi', _f64), ('mu_lo', _f64), ('mu_hi', _f64), ('mu_link', _f64),
         ('grav_mean', _f64), ('grav_std', _f64),
     ]
+
+
+class Tuning(C.Structure):
+    """struct os2r_tuning (zero = defaults)"""
+    _fields_ = [('sort_margin', _f64), ('force_block', _i32), ('force_lone', _i32), ('disable_root_fold', _i32),
+                ('force_scalar', _i32)]
 
 
 class PackedLayout(C.Structure):
@@ -105,7 +112,10 @@ SYMBOLS = {
     'os2r_params_width': (_i32, [C.POINTER(Model)]),
     'os2r_create': (_i32, [C.POINTER(Model), C.POINTER(TaskCfg), C.c_int64, C.c_int64, _i32,
                            C.c_uint64, _i32, C.POINTER(_vp)]),
+    'os2r_create_tuned': (_i32, [C.POINTER(Model), C.POINTER(TaskCfg), C.c_int64, C.c_int64, _i32,
+                                 C.c_uint64, _i32, C.POINTER(Tuning), C.POINTER(_vp)]),
     'os2r_destroy': (_i32, [_vp]),
+    'os2r_set_randomization': (_i32, [_vp, C.POINTER(TaskCfg)]),
     'os2r_seed': (_i32, [_vp, C.c_uint64]),
     'os2r_reset': (_i32, [_vp, _vp, _vp, _vp]),
     'os2r_step': (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
@@ -119,8 +129,11 @@ SYMBOLS = {
     'os2r_set_state': (_i32, [_vp, _vp]),
     'os2r_get_params': (_i32, [_vp, _vp]),
     'os2r_set_params': (_i32, [_vp, _vp]),
-    'os2r_get_episode': (_i32, [_vp, _vp, _vp, _vp]),
+    'os2r_get_episode': (_i32, [_vp, _vp, _vp, _vp, _vp]),
+    'os2r_set_episode': (_i32, [_vp, _vp, _vp, _vp, _vp]),
     'os2r_stats_read': (_i32, [_vp, C.POINTER(Stats), _i32]),
+    'os2r_stats_write': (_i32, [_vp, C.POINTER(Stats)]),
+    'os2r_host_action_buffer': (_i32, [_vp, C.POINTER(C.POINTER(C.c_float))]),
     'os2r_num_envs': (C.c_int64, [_vp]),
     'os2r_obs_dim': (_i32, [_vp]),
     'os2r_kernel_launches': (C.c_int64, [_vp]),

@@ -66,6 +66,13 @@ class CudaVecEnv:
         self.closed = False
         self._pending = None
 
+    @property
+    def action_buffer(self) -> np.ndarray:
+        """Page-locked ``[num_envs, 2]`` float32 array owned by the engine: write the actions here and pass THIS array to
+        ``step`` / ``step_async`` and the host-to-device copy reads it directly (no staging memcpy). Do not write to it
+        between ``step_async`` and ``step_wait``."""
+        return self.runtime.engine.action_buffer
+
     def _out(self, t):
         return t.detach().cpu().numpy() if self.output == 'numpy' else t
 
@@ -80,7 +87,8 @@ class CudaVecEnv:
         if self.output == 'numpy' and not custom:
             # numpy in / numpy out through the C-ABI host entry points: the actions are staged and H2D + kernel + ONE D2H
             # into a pinned block are enqueued now; step_wait only waits (the caller may do other work in between)
-            self.runtime.engine.step_host_packed_begin(np.asarray(actions, dtype=np.float32))
+            a = actions if isinstance(actions, np.ndarray) and actions.dtype == np.float32 else np.asarray(actions, dtype=np.float32)
+            self.runtime.engine.step_host_packed_begin(a)
             self._pending = ('host', None)
         else:
             self._pending = ('device', self.env.step(actions))                # enqueued on the current stream
@@ -123,14 +131,37 @@ class CudaVecEnv:
             self.env.close()
             self.closed = True
 
+    def _get_indices(self, indices):
+        """subproc_vec_env.py:177-189 / vec_env.py:225-245: None = all envs, an int = that env, else an iterable."""
+        if indices is None:
+            return list(range(self.num_envs))
+        if isinstance(indices, (int, np.integer)):
+            indices = [int(indices)]
+        out = [int(i) for i in indices]
+        for i in out:
+            if not -self.num_envs <= i < self.num_envs:
+                raise IndexError(f'env index {i} out of range for {self.num_envs} envs')
+        return out
+
     def get_attr(self, attr_name, indices=None):
-        return [getattr(self.env, attr_name)]
+        """One entry per selected env, as the reference returns (subproc_vec_env.py:150-156). All envs of the batch
+        share ONE task / runtime object, so the entries are the same object."""
+        value = getattr(self.env, attr_name)
+        return [value for _ in self._get_indices(indices)]
 
     def set_attr(self, attr_name, value, indices=None):
+        """The batch shares one runtime: an attribute cannot differ between envs, so only "all envs" is accepted."""
+        if len(self._get_indices(indices)) != self.num_envs:
+            raise ValueError('the envs of a CUDA batch share one runtime object: set_attr applies to all of them '
+                             '(indices=None)')
         setattr(self.runtime, attr_name, value)
 
     def env_method(self, method_name, *args, indices=None, **kwargs):
-        return [getattr(self.env, method_name)(*args, **kwargs)]
+        """Calls the method ONCE on the shared runtime and returns the result once per selected env
+        (subproc_vec_env.py:166-175 returns one result per env)."""
+        idx = self._get_indices(indices)
+        result = getattr(self.env, method_name)(*args, **kwargs)
+        return [result for _ in idx]
 
     @property
     def unwrapped(self):

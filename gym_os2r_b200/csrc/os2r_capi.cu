@@ -59,7 +59,7 @@ void mat_vec(const double *A, const double *x, double *y) { double t[3]; for (in
 // New body frame B' = B*C (C e_x = axis): R_tree' = Cprev^T R_tree C, p_tree' = Cprev^T p_tree,
 // com' = C^T com, I' = C^T I C, contact' = C^T contact.
 template <typename T>
-void build_model_dev(const os2r_model &m, ModelDev<T> &d) {
+void build_model_dev(const os2r_model &m, const os2r_tuning &tune, ModelDev<T> &d) {
     memset(&d, 0, sizeof(d));
     double Cprev[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
     double Cs[OS2R_MAX_DOF][9];
@@ -107,8 +107,7 @@ void build_model_dev(const os2r_model &m, ModelDev<T> &d) {
     d.pgs_iters = m.pgs_iters;
     d.pgs_tol2 = (T)(m.pgs_tol * m.pgs_tol);
     // lane-sorting hint: a proxy within this clearance may touch down during the next env step
-    const char *margin = getenv("OS2R_SORT_MARGIN");
-    d.sort_margin = (T)(margin ? atof(margin) : 0.002);
+    d.sort_margin = (T)(tune.sort_margin > 0.0 ? tune.sort_margin : 0.002);
     // Root body turning about an axis parallel to gravity (z): its contribution to the joint-space dynamics is the
     // constant inertia about that axis (see ModelDev::root_spin). Axis of joint 0 in the world = first column of the
     // normalised tree_R[0]; the tilt tolerance (1e-9 rad) is far below the fp32 kernel's own rounding
@@ -118,7 +117,7 @@ void build_model_dev(const os2r_model &m, ModelDev<T> &d) {
         const bool vertical = fabs(a[0]) < 1e-9 && fabs(a[1]) < 1e-9 && fabs(fabs(a[2]) - 1.0) < 1e-9;
         bool carries_contact = false;
         for (int c = 0; c < m.n_contacts; ++c) carries_contact = carries_contact || m.contact_body[c] == 0;
-        d.root_spin = (vertical && !getenv("OS2R_NO_ROOT_SPIN")) ? 1 : 0;
+        d.root_spin = (vertical && !tune.disable_root_fold) ? 1 : 0;
         (void)carries_contact;   // the proxies' positions are still computed from body 0's frame
         // |a x com|^2 with a = e_x in the normalised body frame: com_y^2 + com_z^2 ; a.I.a = Ixx
         const double cy = (double)d.com[0][1], cz = (double)d.com[0][2];
@@ -334,7 +333,15 @@ int32_t os2r_params_width(const os2r_model *m) { return 3 * m->n_dof + m->n_cont
 
 int32_t os2r_create(const os2r_model *model, const os2r_task_cfg *task, int64_t n_envs, int64_t first_env_id,
                     int32_t device, uint64_t seed, int32_t precision, os2r_env **out) {
+    return os2r_create_tuned(model, task, n_envs, first_env_id, device, seed, precision, nullptr, out);
+}
+
+int32_t os2r_create_tuned(const os2r_model *model, const os2r_task_cfg *task, int64_t n_envs, int64_t first_env_id,
+                          int32_t device, uint64_t seed, int32_t precision, const os2r_tuning *tuning, os2r_env **out) {
     if (!model || !task || !out) return fail("os2r_create: null argument");
+    os2r_tuning tune;
+    memset(&tune, 0, sizeof(tune));
+    if (tuning) tune = *tuning;
     *out = nullptr;
     if (n_envs <= 0) return fail("os2r_create: n_envs must be positive (got %lld)", (long long)n_envs);
     if (model->n_dof < 2 || model->n_dof > OS2R_MAX_DOF) return fail("os2r_create: n_dof %d unsupported (2..5)", model->n_dof);
@@ -360,18 +367,17 @@ int32_t os2r_create(const os2r_model *model, const os2r_task_cfg *task, int64_t 
 
     os2r_env *h = new os2r_env();
     h->sm_count = sm_count;
-    const char *force_block = getenv("OS2R_FORCE_BLOCK");   // experiments only
     h->block = precision == 32 ? step_block_threads<float>(n_envs, sm_count) : step_block_threads<double>(n_envs, sm_count);
-    if (force_block && (atoi(force_block) == OS2R_BLOCK || (precision == 32 && atoi(force_block) == OS2R_BLOCK_WIDE))) h->block = atoi(force_block);
+    if (tune.force_block == OS2R_BLOCK || (precision == 32 && tune.force_block == OS2R_BLOCK_WIDE)) h->block = tune.force_block;
+    else if (tune.force_block != 0) { delete h; return fail("os2r_create: tuning.force_block %d unsupported (%d or %d)", tune.force_block, OS2R_BLOCK, OS2R_BLOCK_WIDE); }
     // up to four 2-warp blocks per SM fit at ~225 registers per thread: every batch that runs on the narrow blocks
     h->lone = precision == 32 && h->block == OS2R_BLOCK && n_envs <= (int64_t)sm_count * 4 * OS2R_BLOCK;
-    const char *force_lone = getenv("OS2R_FORCE_LONE");   // experiments: 0 or 1
-    if (force_lone && precision == 32 && h->block == OS2R_BLOCK) h->lone = atoi(force_lone) != 0;
+    if (tune.force_lone != 0 && precision == 32 && h->block == OS2R_BLOCK) h->lone = tune.force_lone > 0;
     h->model = *model; h->task = *task; h->precision = precision; h->device = device;
     h->n = n_envs; h->first_env_id = first_env_id; h->seed = seed;
     h->rows = model->n_dof + 3 * model->n_contacts;
-    build_model_dev<float>(*model, h->m32);
-    build_model_dev<double>(*model, h->m64);
+    build_model_dev<float>(*model, tune, h->m32);
+    build_model_dev<double>(*model, tune, h->m64);
     memset(&h->taskdev, 0, sizeof(h->taskdev));
     h->taskdev.cfg = *task;
     for (int i = 0; i < model->n_dof; ++i) { h->taskdev.nominal_damping[i] = model->damping[i]; h->taskdev.nominal_friction[i] = model->friction[i]; }
@@ -395,6 +401,8 @@ int32_t os2r_create(const os2r_model *model, const os2r_task_cfg *task, int64_t 
     if ((e = cudaMalloc(&h->cls, n_envs)) != cudaSuccess) return cleanup("cudaMalloc(cls)", e);
     if ((e = cudaMalloc(&h->stats, sizeof(StatsDev))) != cudaSuccess) return cleanup("cudaMalloc(stats)", e);
     if ((e = cudaMemset(h->stats, 0, sizeof(StatsDev))) != cudaSuccess) return cleanup("cudaMemset(stats)", e);
+    e = precision == 32 ? prepare_step<float>(model->n_dof, h->block) : prepare_step<double>(model->n_dof, h->block);
+    if (e != cudaSuccess) return cleanup("cudaFuncSetAttribute(step kernel shared memory)", e);
     if (precision == 32) { carve<float>(h, h->s32); e = launch_init<float>(h->taskdev, h->s32, model->gravity_z, 0); }
     else { carve<double>(h, h->s64); e = launch_init<double>(h->taskdev, h->s64, model->gravity_z, 0); }
     if (e != cudaSuccess) return cleanup("init kernel", e);
@@ -407,6 +415,7 @@ int32_t os2r_create(const os2r_model *model, const os2r_task_cfg *task, int64_t 
 int32_t os2r_destroy(os2r_env *h) {
     if (!h) return 0;
     DeviceGuard guard(h->device);
+    if (h->host_stream) cudaStreamSynchronize(h->host_stream);   // a packed step may still be reading / writing the staging buffers
     cudaFree(h->real_block); cudaFree(h->steps); cudaFree(h->episode); cudaFree(h->reset_id); cudaFree(h->ret); cudaFree(h->cls);
     cudaFree(h->stats);
     if (h->host_io_ready || h->host_stream) {
@@ -460,6 +469,7 @@ int32_t os2r_step_host(os2r_env *h, const float *actions, float *obs, float *rew
                        float *terminal_obs, int32_t *info) {
     if (!h) return fail("os2r_step_host: null handle");
     if (!actions || !obs || !reward || !done) return fail("os2r_step_host: actions/obs/reward/done must be non-null");
+    if (h->packed_pending) return fail("os2r_step_host: a packed step is in flight (call os2r_step_host_packed_end first)");
     DeviceGuard guard(h->device);
     if (ensure_host_io(h)) return 1;
     const int64_t N = h->n;
@@ -619,13 +629,50 @@ int32_t os2r_set_params(os2r_env *h, const double *params_host) {
     CK(cudaDeviceSynchronize());
     return h->precision == 32 ? set_params_impl<float>(h, h->s32, params_host) : set_params_impl<double>(h, h->s64, params_host);
 }
-int32_t os2r_get_episode(os2r_env *h, int32_t *steps_host, double *returns_host, int32_t *reset_ids_host) {
+int32_t os2r_get_episode(os2r_env *h, int32_t *steps_host, double *returns_host, int32_t *reset_ids_host,
+                         uint32_t *episodes_host) {
     if (!h) return fail("os2r_get_episode: null handle");
     DeviceGuard guard(h->device);
     CK(cudaDeviceSynchronize());
     if (steps_host) CK(cudaMemcpy(steps_host, h->steps, h->n * sizeof(int32_t), cudaMemcpyDeviceToHost));
     if (returns_host) CK(cudaMemcpy(returns_host, h->ret, h->n * sizeof(double), cudaMemcpyDeviceToHost));
     if (reset_ids_host) CK(cudaMemcpy(reset_ids_host, h->reset_id, h->n * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    if (episodes_host) CK(cudaMemcpy(episodes_host, h->episode, h->n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    return 0;
+}
+int32_t os2r_set_episode(os2r_env *h, const int32_t *steps_host, const double *returns_host,
+                         const int32_t *reset_ids_host, const uint32_t *episodes_host) {
+    if (!h) return fail("os2r_set_episode: null handle");
+    DeviceGuard guard(h->device);
+    CK(cudaDeviceSynchronize());
+    if (reset_ids_host)
+        for (int64_t e = 0; e < h->n; ++e)
+            if (reset_ids_host[e] < 0 || reset_ids_host[e] >= h->task.n_resets)
+                return fail("os2r_set_episode: reset id %d of env %lld out of range (0..%d)", reset_ids_host[e], (long long)e, h->task.n_resets - 1);
+    if (steps_host) CK(cudaMemcpy(h->steps, steps_host, h->n * sizeof(int32_t), cudaMemcpyHostToDevice));
+    if (returns_host) CK(cudaMemcpy(h->ret, returns_host, h->n * sizeof(double), cudaMemcpyHostToDevice));
+    if (reset_ids_host) CK(cudaMemcpy(h->reset_id, reset_ids_host, h->n * sizeof(int32_t), cudaMemcpyHostToDevice));
+    if (episodes_host) CK(cudaMemcpy(h->episode, episodes_host, h->n * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+int32_t os2r_set_randomization(os2r_env *h, const os2r_task_cfg *cfg) {
+    if (!h || !cfg) return fail("os2r_set_randomization: null argument");
+    if (!(cfg->mass_lo > 0.0) || cfg->mass_hi < cfg->mass_lo) return fail("os2r_set_randomization: mass range must satisfy 0 < lo <= hi");
+    if (cfg->fric_lo < 0.0 || cfg->fric_hi < cfg->fric_lo) return fail("os2r_set_randomization: friction range must satisfy 0 <= lo <= hi");
+    if (cfg->damp_lo < 0.0 || cfg->damp_hi < cfg->damp_lo) return fail("os2r_set_randomization: damping range must satisfy 0 <= lo <= hi");
+    if (cfg->mu_lo < 0.0 || cfg->mu_hi < cfg->mu_lo || cfg->mu_link < 0.0) return fail("os2r_set_randomization: mu range must satisfy 0 <= lo <= hi");
+    if (cfg->grav_std < 0.0 || cfg->gravity_redraw_resets < 0) return fail("os2r_set_randomization: grav_std / gravity_redraw_resets must be >= 0");
+    DeviceGuard guard(h->device);
+    CK(cudaDeviceSynchronize());   // the task configuration is a kernel parameter: steps already enqueued keep the old one
+    os2r_task_cfg &t = h->taskdev.cfg;
+    t.mass_lo = cfg->mass_lo; t.mass_hi = cfg->mass_hi; t.fric_lo = cfg->fric_lo; t.fric_hi = cfg->fric_hi;
+    t.damp_lo = cfg->damp_lo; t.damp_hi = cfg->damp_hi; t.mu_lo = cfg->mu_lo; t.mu_hi = cfg->mu_hi; t.mu_link = cfg->mu_link;
+    t.grav_mean = cfg->grav_mean; t.grav_std = cfg->grav_std;
+    t.reset_randomized = cfg->reset_randomized; t.randomize_params = cfg->randomize_params;
+    t.randomize_gravity = cfg->randomize_gravity; t.gravity_redraw_resets = cfg->gravity_redraw_resets;
+    h->task = t;
+    // a damping range on a model with damped joints keeps the implicit-damping build; nothing else depends on the ranges
     return 0;
 }
 
@@ -639,6 +686,26 @@ int32_t os2r_stats_read(os2r_env *h, os2r_stats *out, int32_t clear) {
     out->episodes = s.episodes; out->done_task = s.done_task; out->done_timelimit = s.done_timelimit;
     out->nonfinite_resets = s.nonfinite_resets; out->sum_return = s.sum_return; out->sum_length = s.sum_length;
     if (clear) { CK(cudaMemset(h->stats, 0, sizeof(StatsDev))); h->env_steps = 0; }
+    return 0;
+}
+
+int32_t os2r_stats_write(os2r_env *h, const os2r_stats *in) {
+    if (!h || !in) return fail("os2r_stats_write: null argument");
+    DeviceGuard guard(h->device);
+    CK(cudaDeviceSynchronize());
+    StatsDev s;
+    s.episodes = in->episodes; s.done_task = in->done_task; s.done_timelimit = in->done_timelimit;
+    s.nonfinite_resets = in->nonfinite_resets; s.sum_return = in->sum_return; s.sum_length = in->sum_length;
+    CK(cudaMemcpy(h->stats, &s, sizeof(s), cudaMemcpyHostToDevice));
+    h->env_steps = in->env_steps;
+    return 0;
+}
+
+int32_t os2r_host_action_buffer(os2r_env *h, float **actions_out) {
+    if (!h || !actions_out) return fail("os2r_host_action_buffer: null argument");
+    DeviceGuard guard(h->device);
+    if (ensure_host_io(h)) return 1;
+    *actions_out = h->pin_actions;
     return 0;
 }
 

@@ -242,7 +242,8 @@ __device__ inline void rng_normal2(uint64_t seed, uint64_t env_id, uint32_t epis
     z[0] = r * c; z[1] = r * s;
 }
 enum { DRAW_RESET = 0, DRAW_PITCH = 1, DRAW_NOISE = 2, DRAW_LAYSIDE = 4, DRAW_DIR = 5, DRAW_YAW = 6,
-       DRAW_SIMPLE_HIP = 7, DRAW_SIMPLE_KNEE = 8, DRAW_PARAMS = 10 };
+       DRAW_SIMPLE_HIP = 7, DRAW_SIMPLE_KNEE = 8, DRAW_PARAMS = 10 /* .. 10 + 3*MAX_DOF + MAX_CONTACTS */,
+       DRAW_GRAVITY = 40 /*,41*/ };
 #define OS2R_EPISODE_GRAVITY 0xFFFFFFFFu
 
 // ------------------------------------------------------------------------------------------------
@@ -805,6 +806,13 @@ __device__ inline void draw_params(const TaskDev &K, StateDev<T> &S, int64_t e, 
         if (C.randomize_params)
             mu = C.mu_link * (C.mu_lo + (C.mu_hi - C.mu_lo) * rng_uniform(S.seed, gid, ep, DRAW_PARAMS + 3 * OS2R_MAX_DOF + c));
         S.mu[c * N + e] = (T)mu;
+    }
+    // MonopodEnvRandomizer(num_physics_rollouts=K): randomize_physics again at every K-th reset of the env
+    // (randomizers/monopod.py:36,56-61,371)
+    if (C.randomize_gravity && C.gravity_redraw_resets > 0 && ep % (uint32_t)C.gravity_redraw_resets == 0) {
+        double z[2];
+        rng_normal2(S.seed, gid, ep, DRAW_GRAVITY, z);
+        S.gravity_z[e] = (T)(C.grav_mean + C.grav_std * z[0]);
     }
 }
 

@@ -203,8 +203,12 @@ step_kernel(const __grid_constant__ ModelDev<T> M, const __grid_constant__ TaskD
     int reset_idx = __ldcg(S.reset_id + e);
     const double ret_in = __ldcg(S.ret + e);
     float2 act = __ldcg(reinterpret_cast<const float2 *>(actions) + e);
-    // ScenarIO clips force targets to +-max force (tasks/monopod.py:313-316); a NaN action is left to
-    // the non-finite guard below.
+    // A non-finite action (the reference rejects it through `assert action_space.contains`, tasks/monopod.py:218)
+    // applies no torque and takes the non-finite path of the epilogue: defined outputs, forced reset, counted.
+    // fminf / fmaxf would silently turn a NaN into a full negative torque.
+    const bool act_finite = isfinite(act.x) && isfinite(act.y);
+    if (!act_finite) { act.x = 0.0f; act.y = 0.0f; }
+    // ScenarIO clips force targets to +-max force (tasks/monopod.py:313-316)
     act.x = fminf(1.0f, fmaxf(-1.0f, act.x));
     act.y = fminf(1.0f, fmaxf(-1.0f, act.y));
 #pragma unroll
@@ -245,21 +249,25 @@ step_kernel(const __grid_constant__ ModelDev<T> M, const __grid_constant__ TaskD
 
     // ---- epilogue (fp64, once per env step) --------------------------------------------------------
     double q[N], v[N];
-    bool finite = true;
+    bool finite = act_finite;
 #pragma unroll
     for (int i = 0; i < N; ++i) {
         q[i] = (double)E.q_hi[i] + (double)C(SL::QLO + i);
         v[i] = (double)E.v[i] + (double)C(SL::VLO + i);
         finite = finite && isfinite(q[i]) && isfinite(v[i]);
     }
+    if (!finite) {   // nothing non-finite leaves the kernel: the step reports a zero observation and reward
+#pragma unroll
+        for (int i = 0; i < N; ++i) { q[i] = 0.0; v[i] = 0.0; }
+    }
     const double a0[2] = {(double)act.x, (double)act.y};
     const double a_old[2] = {(double)C(SL::AOLD), (double)C(SL::AOLD + 1)};
     double o[OS2R_MAX_OBS];
     const bool task_done = observe<N>(K, q, v, a_old, o);
-    const double r = reward_fn(K.cfg, o, a0, a_old);
+    const double r = finite ? reward_fn(K.cfg, o, a0, a_old) : 0.0;
     const int D = K.cfg.obs_dim;
-    int cause = task_done ? 1 : 0;
-    if (!finite) cause |= 4;
+    int cause = (task_done && finite) ? 1 : 0;
+    if (!finite) cause = 4;
     const int steps = __float_as_int_t<T>(C(SL::MISC)) + 1;
     const double ret = __hiloint2double(__float_as_int_t<T>(C(SL::MISC + 2)), __float_as_int_t<T>(C(SL::MISC + 1))) + r;
     if (K.cfg.max_episode_steps > 0 && steps >= K.cfg.max_episode_steps) cause |= 2;
@@ -371,14 +379,8 @@ static cudaError_t launch_step_nd(const ModelDev<T> &M, const TaskDev &K, const 
             return cudaGetLastError();
         }
     }
-    if (smem > 48 * 1024) {
-        static bool raised = false;   // per kernel instantiation
-        if (!raised) {
-            cudaError_t e = cudaFuncSetAttribute(step_kernel<T, N, OS2R_NC, BLOCK, DAMPED, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e != cudaSuccess) return e;
-            raised = true;
-        }
-    }
+    // blocks that need more than 48 KB of dynamic shared memory were opted in by prepare_step (once per handle,
+    // on the handle's device: the attribute is per device, a process can hold handles on several GPUs)
     step_kernel<T, N, OS2R_NC, BLOCK, DAMPED, false><<<grid_for(S.n_envs, BLOCK), BLOCK, smem, stream>>>(M, K, S, io, stats);
     return cudaGetLastError();
 }
@@ -448,6 +450,32 @@ cudaError_t step_kernel_attributes(int n_dof, int block, bool damped, cudaFuncAt
     return cudaErrorInvalidValue;
 }
 
+template <typename T, int N, int BLOCK, bool DAMPED>
+static cudaError_t prepare_nd() {
+    constexpr size_t smem = step_smem_bytes<T, N, BLOCK>();
+    if (smem <= 48 * 1024) return cudaSuccess;
+    return cudaFuncSetAttribute(step_kernel<T, N, OS2R_NC, BLOCK, DAMPED, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+}
+template <typename T, int N, int BLOCK>
+static cudaError_t prepare_n() {
+    cudaError_t e = prepare_nd<T, N, BLOCK, true>();
+    if (e != cudaSuccess) return e;
+    if constexpr (sizeof(T) == 4) return prepare_nd<T, N, BLOCK, false>();
+    return cudaSuccess;
+}
+// Opt the step kernels this handle can launch (damped and undamped build) into their dynamic shared memory size on the
+// CURRENT device. Called by os2r_create under its device guard.
+template <typename T>
+cudaError_t prepare_step(int n_dof, int block) {
+    if (sizeof(T) == 4 && block == OS2R_BLOCK_WIDE) {
+        if constexpr (sizeof(T) == 4) {
+            OS2R_DISPATCH_N(n_dof, return (prepare_n<T, N_, OS2R_BLOCK_WIDE>()));
+        }
+    }
+    OS2R_DISPATCH_N(n_dof, return (prepare_n<T, N_, OS2R_BLOCK>()));
+    return cudaErrorInvalidValue;
+}
+
 cudaError_t launch_fma_peak(float *out, int blocks, int iters, cudaStream_t stream) {
     fma_peak_kernel<<<blocks, 256, 0, stream>>>(out, iters, 1.0f);
     return cudaGetLastError();
@@ -460,7 +488,8 @@ cudaError_t launch_fma_peak(float *out, int blocks, int iters, cudaStream_t stre
     template cudaError_t launch_reset<T>(int, int, const TaskDev &, const StateDev<T> &, const uint8_t *,     \
                                          float *, cudaStream_t);                                              \
     template cudaError_t launch_init<T>(const TaskDev &, const StateDev<T> &, double, cudaStream_t);          \
-    template cudaError_t step_kernel_attributes<T>(int, int, bool, cudaFuncAttributes *, int *);
+    template cudaError_t step_kernel_attributes<T>(int, int, bool, cudaFuncAttributes *, int *);            \
+    template cudaError_t prepare_step<T>(int, int);
 OS2R_INSTANTIATE(float)
 OS2R_INSTANTIATE(double)
 

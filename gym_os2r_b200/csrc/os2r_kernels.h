@@ -31,6 +31,8 @@ template <typename T>
 cudaError_t launch_init(const TaskDev &K, const StateDev<T> &S, double nominal_gz, cudaStream_t stream);
 template <typename T>
 cudaError_t step_kernel_attributes(int n_dof, int block, bool damped, cudaFuncAttributes *attr, int *blocks_per_sm);
+template <typename T>
+cudaError_t prepare_step(int n_dof, int block);
 cudaError_t launch_fma_peak(float *out, int blocks, int iters, cudaStream_t stream);
 
 }  // namespace os2r

@@ -48,8 +48,13 @@ class MonopodEnvRandomizer(Wrapper, MonopodRandomizersMixin):
     def __init__(self, env: Callable, num_physics_rollouts: int = 0, **kwargs):
         MonopodRandomizersMixin.__init__(self, randomize_physics_after_rollouts=num_physics_rollouts)
         Wrapper.__init__(self, env() if callable(env) else env)
+        if int(num_physics_rollouts) < 0:
+            raise ValueError('num_physics_rollouts must be >= 0')
+        # num_physics_rollouts = K > 0: gravity is drawn again at every K-th reset of an env (reference :36,56-61,371:
+        # PhysicsRandomizer.physics_expired); 0 = drawn once at construction
         self.env.unwrapped.configure_randomization(reset_randomized=True, randomize_params=True,
-                                                   randomize_gravity=True, randomization=dict(self.randomization))
+                                                   randomize_gravity=True, randomization=dict(self.randomization),
+                                                   gravity_redraw_resets=int(num_physics_rollouts))
 
     def get_state_info(self, state, actions):
         return self.env.unwrapped.task.get_state_info(state, actions)

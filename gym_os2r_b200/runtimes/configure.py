@@ -9,6 +9,7 @@ from ..tasks.monopod import build_task_cfg
 def configure(task_cls, agent_rate: float = 1000, physics_rate: float = 10000, *,
               max_episode_steps: int = 0, auto_reset: bool = False, reset_randomized: bool = False,
               randomize_params: bool = False, randomize_gravity: bool = False, randomization: dict = None,
+              gravity_redraw_resets: int = 0,
               pgs_iters: int = None, pgs_tol: float = None, substeps: int = None, **task_kwargs) -> Tuple[object, compiler.CompiledModel, _capi.TaskCfg]:
     """Create the task, its spaces, the compiled model tables and the device task configuration."""
     task = task_cls(agent_rate=agent_rate, **task_kwargs)
@@ -24,5 +25,6 @@ def configure(task_cls, agent_rate: float = 1000, physics_rate: float = 10000, *
     compiled = compiler.compile_model(model_name, physics, max_torque=tuple(task.max_torques))
     cfg = build_task_cfg(task, compiled, max_episode_steps=max_episode_steps, auto_reset=auto_reset,
                          reset_randomized=reset_randomized, randomize_params=randomize_params,
-                         randomize_gravity=randomize_gravity, randomization=randomization)
+                         randomize_gravity=randomize_gravity, randomization=randomization,
+                         gravity_redraw_resets=gravity_redraw_resets)
     return task, compiled, cfg

@@ -36,7 +36,7 @@ class CudaRuntime(Env):
                  physics_engine=None, world: str = None, num_envs: int = 1, device: int = 0,
                  seed: Optional[int] = None, max_episode_steps: int = 0, auto_reset: Optional[bool] = None,
                  precision: int = 32, first_env_id: int = 0, pgs_iters: Optional[int] = None, pgs_tol: Optional[float] = None,
-                 **kwargs):
+                 tuning: Optional[dict] = None, **kwargs):
         steps = physics_rate / agent_rate
         if steps != int(steps):
             warnings.warn(f'Rounding the number of iterations to {int(steps)} from the nominal {steps}')
@@ -48,11 +48,12 @@ class CudaRuntime(Env):
         self._seed = 0 if seed is None else int(seed)
         self._precision = int(precision)
         self._first_env_id = int(first_env_id)
+        self._tuning = dict(tuning) if tuning else None
         self._task_cls, self._task_kwargs = task_cls, dict(kwargs)
         self._opts = dict(max_episode_steps=int(max_episode_steps or 0),
                           auto_reset=self.batched if auto_reset is None else bool(auto_reset),
                           reset_randomized=False, randomize_params=False, randomize_gravity=False,
-                          randomization=None, pgs_iters=pgs_iters, pgs_tol=pgs_tol)
+                          randomization=None, gravity_redraw_resets=0, pgs_iters=pgs_iters, pgs_tol=pgs_tol)
         self._engine: Optional[Engine] = None
         self._build_task()
         self._gazebo = SimulatorShim(self)
@@ -60,6 +61,8 @@ class CudaRuntime(Env):
         self._out = {}
         self._staged = None
         self._prev_actions = None
+        self._custom_returns = None       # per-episode returns of a user-defined reward (device tensor)
+        self._custom_sum_return = None
         self.spec = None
 
     # ------------------------------------------------------------------ configuration
@@ -77,26 +80,29 @@ class CudaRuntime(Env):
         self.action_space.seed(self._seed)
 
     def configure_randomization(self, *, reset_randomized=None, randomize_params=None, randomize_gravity=None,
-                                randomization=None):
+                                randomization=None, gravity_redraw_resets=None):
         """Called by the env randomizer wrappers before the first reset (reference: the wrappers own
-        ``randomize_task`` / ``randomize_physics`` / ``randomize_model_description``)."""
+        ``randomize_task`` / ``randomize_physics`` / ``randomize_model_description``). On a live engine the new
+        ranges / switches are applied in place (``os2r_set_randomization``) and take effect at the next resets."""
         changed = False
         for key, val in (('reset_randomized', reset_randomized), ('randomize_params', randomize_params),
-                         ('randomize_gravity', randomize_gravity), ('randomization', randomization)):
+                         ('randomize_gravity', randomize_gravity), ('randomization', randomization),
+                         ('gravity_redraw_resets', gravity_redraw_resets)):
             if val is not None and self._opts[key] != val:
                 self._opts[key] = val
                 changed = True
         if changed:
-            if self._engine is not None:
-                self._engine.close()
-                self._engine = None
             self._build_task()
+            if self._engine is not None:
+                self._engine.set_randomization(self._cfg)
+                self._engine.task_cfg = self._cfg
 
     @property
     def engine(self) -> Engine:
         if self._engine is None:
             self._engine = Engine(self._compiled, self._cfg, self.num_envs, device=self.device_index,
-                                  seed=self._seed, first_env_id=self._first_env_id, precision=self._precision)
+                                  seed=self._seed, first_env_id=self._first_env_id, precision=self._precision,
+                                  tuning=self._tuning)
         return self._engine
 
     # properties the reference exposes
@@ -151,12 +157,20 @@ class CudaRuntime(Env):
             a = torch.as_tensor(arr.astype(np.float32), device=eng.device).reshape(1, 2)
         obs, reward, done_u8, info_t = eng.step(a)
         if custom:
-            # user-defined RewardBase subclass: batched torch evaluation on the device
+            # User-defined RewardBase subclass: one batched torch evaluation on the device, on the observation the
+            # step produced BEFORE any auto-reset (terminal_obs equals obs for envs that did not finish). The kernel
+            # accumulated reward 0, so the per-episode returns and their statistics are kept here.
             prev = self._prev_actions if self._prev_actions is not None else torch.zeros_like(a)
-            src = eng.terminal_obs if self._cfg.auto_reset else obs
-            r = self.task.reward.calculate_reward(src.double(), [a.double(), prev.double()])
+            r = self.task.reward.calculate_reward(eng.terminal_obs.double(), [a.double(), prev.double()])
             reward = torch.as_tensor(r, device=eng.device, dtype=torch.float32).expand(self.num_envs).contiguous()
             eng.reward.copy_(reward)
+            if self._custom_returns is None:
+                self._custom_returns = torch.zeros(self.num_envs, dtype=torch.float64, device=eng.device)
+                self._custom_sum_return = torch.zeros((), dtype=torch.float64, device=eng.device)
+            self._custom_returns += reward.double()
+            fin = done_u8.bool()
+            self._custom_sum_return += (self._custom_returns * fin).sum()
+            self._custom_returns.masked_fill_(fin, 0.0)
         self._prev_actions = a.clone()
         self._out = {'obs': obs, 'reward': reward, 'done': done_u8.bool()}
         if self.batched:
@@ -212,14 +226,46 @@ class CudaRuntime(Env):
             self._engine.close()
             self._engine = None
 
+    def stats(self, clear: bool = False) -> dict:
+        """Device-side episode statistics (``os2r_stats_read``). With a user-defined reward class the returns are
+        accumulated by this runtime (the kernel saw reward 0) and substituted here."""
+        st = self.engine.stats(clear)
+        if self._custom_sum_return is not None:
+            st['sum_return'] = float(self._custom_sum_return.item())
+            if clear:
+                self._custom_sum_return.zero_()
+        return st
+
     # ------------------------------------------------------------------ checkpoint / resume
     def get_state(self):
+        """Everything needed to continue the rollout in a NEW runtime: joint state + warm-start impulses + last
+        action, the randomised parameters, and the per-env bookkeeping — TimeLimit clocks, episode returns, reset
+        ids and the episode counters that key each env's RNG stream — plus the seed and the statistics."""
         eng = self.engine
         steps, ret = eng.get_episode()
-        return {'state': eng.get_state(), 'params': eng.get_params(), 'steps': steps, 'returns': ret}
+        snap = {'state': eng.get_state(), 'params': eng.get_params(), 'steps': steps, 'returns': ret,
+                'reset_ids': eng.get_reset_ids(), 'episodes': eng.get_episode_counters(), 'seed': self._seed,
+                'stats': eng.stats()}
+        if self._custom_returns is not None:
+            snap['custom_returns'] = self._custom_returns.cpu().numpy()
+            snap['custom_sum_return'] = float(self._custom_sum_return.item())
+        if self._prev_actions is not None:
+            snap['prev_actions'] = self._prev_actions.cpu().numpy()
+        return snap
 
     def set_state(self, snapshot):
         eng = self.engine
+        if 'seed' in snapshot:
+            self.seed(int(snapshot['seed']))
         eng.set_state(snapshot['state'])
         if 'params' in snapshot:
             eng.set_params(snapshot['params'])
+        eng.set_episode(snapshot.get('steps'), snapshot.get('returns'), snapshot.get('reset_ids'),
+                        snapshot.get('episodes'))
+        if 'stats' in snapshot:
+            eng.set_stats(snapshot['stats'])
+        if 'custom_returns' in snapshot:
+            self._custom_returns = torch.as_tensor(snapshot['custom_returns'], device=eng.device, dtype=torch.float64).clone()
+            self._custom_sum_return = torch.tensor(snapshot['custom_sum_return'], device=eng.device, dtype=torch.float64)
+        if 'prev_actions' in snapshot:
+            self._prev_actions = torch.as_tensor(snapshot['prev_actions'], device=eng.device, dtype=torch.float32).clone()

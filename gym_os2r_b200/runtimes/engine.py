@@ -18,7 +18,7 @@ class Engine:
     """
 
     def __init__(self, compiled_model, task_cfg: _capi.TaskCfg, n_envs: int, device: int = 0, seed: int = 0,
-                 first_env_id: int = 0, precision: int = 32):
+                 first_env_id: int = 0, precision: int = 32, tuning: dict = None):
         self.lib = _capi.load_library()
         if not torch.cuda.is_available():
             raise _capi.Os2rError('no CUDA device visible to torch; the monopod step path has no CPU fallback')
@@ -35,9 +35,10 @@ class Engine:
         torch.cuda.init()
         with torch.cuda.device(self.device):
             torch.zeros(1, device=self.device)        # make sure the primary context exists
-            _capi.check(self.lib.os2r_create(C.byref(self.model), C.byref(task_cfg), self.n_envs, int(first_env_id),
-                                             self.device_index, int(seed) & (2 ** 64 - 1), int(precision),
-                                             C.byref(handle)), self.lib)
+            tune = _capi.Tuning(**(tuning or {}))      # scheduling / verification knobs; never change a result
+            _capi.check(self.lib.os2r_create_tuned(C.byref(self.model), C.byref(task_cfg), self.n_envs,
+                                                   int(first_env_id), self.device_index, int(seed) & (2 ** 64 - 1),
+                                                   int(precision), C.byref(tune), C.byref(handle)), self.lib)
         self.handle = handle
         N, D = self.n_envs, self.obs_dim
         kw = dict(device=self.device)
@@ -49,6 +50,7 @@ class Engine:
         self._host_pool = {}
         self._packed_layouts = {}
         self._packed_inflight = None
+        self._action_buffer = None
 
     # ------------------------------------------------------------------ lifecycle
     def close(self):
@@ -105,6 +107,17 @@ class Engine:
         if len(pool) < 64:
             pool.append(arr)
         return arr
+
+    @property
+    def action_buffer(self) -> np.ndarray:
+        """The handle's page-locked ``[N, 2]`` float32 action array (``os2r_host_action_buffer``). A caller that writes
+        its actions here and passes THIS array to ``step_host`` / ``step_host_packed*`` skips the staging memcpy: the
+        host-to-device copy reads it directly. Do not write to it between ``step_host_packed_begin`` and ``_end``."""
+        if self._action_buffer is None:
+            ptr = C.POINTER(C.c_float)()
+            _capi.check(self.lib.os2r_host_action_buffer(self.handle, C.byref(ptr)), self.lib)
+            self._action_buffer = np.ctypeslib.as_array(ptr, shape=(self.n_envs, 2))
+        return self._action_buffer
 
     def step_host(self, actions: np.ndarray, want_terminal_obs: bool = False, want_info: bool = False):
         """numpy in / numpy out: H2D + kernel + D2H inside os2r_step_host. Returned arrays belong to the caller."""
@@ -194,13 +207,38 @@ class Engine:
         steps = np.empty(self.n_envs, dtype=np.int32)
         ret = np.empty(self.n_envs, dtype=np.float64)
         _capi.check(self.lib.os2r_get_episode(self.handle, steps.ctypes.data_as(C.c_void_p),
-                                              ret.ctypes.data_as(C.c_void_p), None), self.lib)
+                                              ret.ctypes.data_as(C.c_void_p), None, None), self.lib)
         return steps, ret
 
     def get_reset_ids(self) -> np.ndarray:
         ids = np.empty(self.n_envs, dtype=np.int32)
-        _capi.check(self.lib.os2r_get_episode(self.handle, None, None, ids.ctypes.data_as(C.c_void_p)), self.lib)
+        _capi.check(self.lib.os2r_get_episode(self.handle, None, None, ids.ctypes.data_as(C.c_void_p), None), self.lib)
         return ids
+
+    def get_episode_counters(self) -> np.ndarray:
+        """Per-env episode counter = counter word of the env's RNG stream (checkpoint / resume)."""
+        ep = np.empty(self.n_envs, dtype=np.uint32)
+        _capi.check(self.lib.os2r_get_episode(self.handle, None, None, None, ep.ctypes.data_as(C.c_void_p)), self.lib)
+        return ep
+
+    def set_episode(self, steps=None, returns=None, reset_ids=None, episodes=None):
+        """``os2r_set_episode``: restore the per-env bookkeeping (any argument may be None = unchanged)."""
+        def arr(x, dt):
+            if x is None:
+                return None, None
+            a = np.ascontiguousarray(x, dtype=dt)
+            assert a.shape == (self.n_envs,), a.shape
+            return a, a.ctypes.data_as(C.c_void_p)
+        keep = [arr(steps, np.int32), arr(returns, np.float64), arr(reset_ids, np.int32), arr(episodes, np.uint32)]
+        _capi.check(self.lib.os2r_set_episode(self.handle, *[p for _, p in keep]), self.lib)
+
+    def set_randomization(self, task_cfg: _capi.TaskCfg):
+        """``os2r_set_randomization``: new ranges / switches for the draws made at the next resets."""
+        _capi.check(self.lib.os2r_set_randomization(self.handle, C.byref(task_cfg)), self.lib)
+
+    def set_stats(self, stats: dict):
+        s = _capi.Stats(**{k: stats[k] for k, _ in _capi.Stats._fields_})
+        _capi.check(self.lib.os2r_stats_write(self.handle, C.byref(s)), self.lib)
 
     def stats(self, clear: bool = False) -> dict:
         s = _capi.Stats()

@@ -254,7 +254,7 @@ RANDOMIZATION_DEFAULTS = dict(   # gym_os2r/randomizers/monopod.py:182-215,58
 
 def build_task_cfg(task: MonopodTask, compiled_model, *, max_episode_steps: int, auto_reset: bool,
                    reset_randomized: bool, randomize_params: bool, randomize_gravity: bool,
-                   randomization: dict = None) -> _capi.TaskCfg:
+                   randomization: dict = None, gravity_redraw_resets: int = 0) -> _capi.TaskCfg:
     """Translate a created task (``create_spaces`` already called) into the device configuration."""
     t = _capi.TaskCfg()
     D = len(task.observation_mask)
@@ -269,6 +269,9 @@ def build_task_cfg(task: MonopodTask, compiled_model, *, max_episode_steps: int,
     t.randomize_params = int(randomize_params)
     t.randomize_gravity = int(randomize_gravity)
     t.simple_sample_reset = int(task.task_mode == 'simple' and not reset_randomized)
+    if int(gravity_redraw_resets) < 0:
+        raise ValueError('num_physics_rollouts must be >= 0')
+    t.gravity_redraw_resets = int(gravity_redraw_resets)   # MonopodEnvRandomizer(num_physics_rollouts=K)
 
     nj = len(task.joint_names)
     col = lambda name: task.observation_index.get(name, -1)

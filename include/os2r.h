@@ -26,10 +26,10 @@
 extern "C" {
 #endif
 
-#define OS2R_ABI_VERSION 7
+#define OS2R_ABI_VERSION 8
 
 #define OS2R_MAX_DOF 5
-#define OS2R_MAX_CONTACTS 4
+#define OS2R_MAX_CONTACTS 6
 #define OS2R_MAX_OBS 12
 #define OS2R_MAX_RESETS 8
 #define OS2R_MAX_ROWS (OS2R_MAX_DOF + 3 * OS2R_MAX_CONTACTS)
@@ -109,6 +109,10 @@ typedef struct os2r_task_cfg {
     int32_t randomize_params;         /* 1: per-reset mass/friction/damping/mu draws             */
     int32_t randomize_gravity;        /* 1: g_z ~ N(mean,std) drawn once per env at creation     */
     int32_t simple_sample_reset;      /* `simple` mode + NoRandomizer: hip,knee ~ obs space      */
+    int32_t gravity_redraw_resets;    /* K > 0: g_z is re-drawn at every K-th reset of an env
+                                         (MonopodEnvRandomizer(num_physics_rollouts=K),
+                                         randomizers/monopod.py:36,56-61,371); 0: drawn once       */
+    int32_t _pad1;
     int32_t reward_pitch_col, reward_yawvel_col, reward_hip_col, reward_knee_col; /* or -1       */
     int32_t obs_kind[OS2R_MAX_OBS];
     int32_t obs_index[OS2R_MAX_OBS];  /* chain dof index (POS/VEL) or action index (TORQUE)      */
@@ -161,7 +165,28 @@ int32_t os2r_params_width(const os2r_model *model);
 int32_t os2r_create(const os2r_model *model, const os2r_task_cfg *task, int64_t n_envs,
                     int64_t first_env_id, int32_t device, uint64_t seed, int32_t precision,
                     os2r_env **out);
+/* Scheduling / debugging knobs that never change what an env computes (they replace the getenv switches of ABI v7).
+ * Zero-initialise for the defaults. */
+typedef struct os2r_tuning {
+    double sort_margin;        /* ground clearance (m) below which a contact proxy counts as "near" for the lane sort;
+                                  <= 0: default 0.002                                                              */
+    int32_t force_block;       /* threads per block of the step kernel; 0: chosen from the batch size            */
+    int32_t force_lone;        /* -1 / +1: force the build without / with an occupancy target off / on; 0: auto  */
+    int32_t disable_root_fold; /* 1: run the general per-body code for the yaw pivot (verification of the fold)  */
+    int32_t force_scalar;      /* 1: one env per thread even where the paired (two envs per thread, packed
+                                  f32x2) build would be chosen                                                    */
+} os2r_tuning;
+/* os2r_create with explicit tuning (NULL = defaults = os2r_create). */
+int32_t os2r_create_tuned(const os2r_model *model, const os2r_task_cfg *task, int64_t n_envs,
+                          int64_t first_env_id, int32_t device, uint64_t seed, int32_t precision,
+                          const os2r_tuning *tuning, os2r_env **out);
 int32_t os2r_destroy(os2r_env *env);
+
+/* Replace the randomisation ranges / switches of a live handle (mass_lo..grav_std, reset_randomized,
+ * randomize_params, randomize_gravity, gravity_redraw_resets of `cfg`; everything else in `cfg` is ignored). Takes
+ * effect from the next reset of each env. Replaces editing MonopodRandomizersMixin's randomization_config
+ * (randomizers/monopod.py:182-215). */
+int32_t os2r_set_randomization(os2r_env *env, const os2r_task_cfg *cfg);
 
 /* env.seed(seed): re-key the RNG streams (runtime seed(), tests/tests_general.py:20). */
 int32_t os2r_seed(os2r_env *env, uint64_t seed);
@@ -226,9 +251,20 @@ int32_t os2r_get_params(os2r_env *env, double *params_host);
 int32_t os2r_set_params(os2r_env *env, const double *params_host);
 /* Per-env episode bookkeeping: steps[N] (int32), returns[N] (double), reset_ids[N] (int32 index
  * into the task's reset_positions = info['reset_orientation'], tasks/monopod.py:374). Any may be NULL. */
-int32_t os2r_get_episode(os2r_env *env, int32_t *steps_host, double *returns_host, int32_t *reset_ids_host);
+int32_t os2r_get_episode(os2r_env *env, int32_t *steps_host, double *returns_host, int32_t *reset_ids_host,
+                         uint32_t *episodes_host);
+/* Restore the bookkeeping (checkpoint / resume into a NEW handle): `episodes` is the per-env episode counter = the
+ * counter word of the env's RNG stream, so a restored env draws the same reset poses / parameters it would have
+ * drawn without the interruption. Any pointer may be NULL (left unchanged). */
+int32_t os2r_set_episode(os2r_env *env, const int32_t *steps_host, const double *returns_host,
+                         const int32_t *reset_ids_host, const uint32_t *episodes_host);
 
 int32_t os2r_stats_read(os2r_env *env, os2r_stats *out, int32_t clear);
+int32_t os2r_stats_write(os2r_env *env, const os2r_stats *in); /* checkpoint / resume */
+
+/* Page-locked host array [N,2] float32 owned by the handle: a caller that writes its actions HERE and passes this
+ * pointer to os2r_step_host / os2r_step_host_packed(_begin) skips the staging memcpy (the H2D copy reads it directly). */
+int32_t os2r_host_action_buffer(os2r_env *env, float **actions_out);
 
 /* Introspection used by bench/tests. */
 int64_t os2r_num_envs(const os2r_env *env);

@@ -85,7 +85,7 @@ static void rng_normal2(uint64_t seed, uint64_t env_id, uint32_t episode, uint32
 }
 /* draw indices (shared with the CUDA kernels) */
 enum { DRAW_RESET = 0, DRAW_PITCH = 1, DRAW_NOISE = 2 /*,3*/, DRAW_LAYSIDE = 4, DRAW_DIR = 5, DRAW_YAW = 6,
-       DRAW_SIMPLE_HIP = 7, DRAW_SIMPLE_KNEE = 8, DRAW_PARAMS = 10 };
+       DRAW_SIMPLE_HIP = 7, DRAW_SIMPLE_KNEE = 8, DRAW_PARAMS = 10 /* .. 10 + 3*NMAX + CMAX */, DRAW_GRAVITY = 40 /*,41*/ };
 #define EPISODE_GRAVITY 0xFFFFFFFFu
 
 /* ------------------------------------------------------------------------------------------ */
@@ -565,6 +565,12 @@ static void reset_env(const os2r_model *M, const os2r_task_cfg *T, uint64_t seed
     if (M->role_dof[OS2R_ROLE_HIP] >= 0) q[M->role_dof[OS2R_ROLE_HIP]] = leg[0];
     if (M->role_dof[OS2R_ROLE_KNEE] >= 0) q[M->role_dof[OS2R_ROLE_KNEE]] = leg[1];
     draw_params(M, T, seed, gid, ep, prow);
+    /* MonopodEnvRandomizer(num_physics_rollouts=K): randomize_physics again at every K-th reset
+     * (randomizers/monopod.py:36,56-61,371; gym-ignition's physics_expired counter) */
+    if (T->randomize_gravity && T->gravity_redraw_resets > 0 && ep % (uint32_t)T->gravity_redraw_resets == 0) {
+        double z[2]; rng_normal2(seed, gid, ep, DRAW_GRAVITY, z);
+        prow[3*n + M->n_contacts] = T->grav_mean + T->grav_std * z[0];
+    }
 }
 
 /* ------------------------------------------------------------------------------------------ */
@@ -615,14 +621,19 @@ static void *step_range(void *arg) {
         double *srow = J->state + e * W, *q = srow, *v = srow + n, *lam = srow + 2*n, *a_prev = srow + 2*n + rows;
         env_params P; unpack_params(M, J->params + e * PW, &P);
         double a[2] = {J->actions[2*e], J->actions[2*e + 1]}, a_old[2] = {a_prev[0], a_prev[1]};
+        /* a non-finite action (rejected by the reference's assert, tasks/monopod.py:218) applies no torque and takes
+         * the non-finite path: zero observation / reward, forced reset; valid ones are clipped to the force limits */
+        int finite = isfinite(a[0]) && isfinite(a[1]);
+        if (!finite) { a[0] = 0; a[1] = 0; }
+        for (int k = 0; k < 2; ++k) { if (a[k] > 1) a[k] = 1; if (a[k] < -1) a[k] = -1; }
         for (int s = 0; s < M->substeps; ++s) substep(M, &P, q, v, lam, a, M->pgs_iters, M->pgs_tol);
+        for (int i = 0; i < n; ++i) if (!isfinite(q[i]) || !isfinite(v[i])) finite = 0;
+        if (!finite) for (int i = 0; i < n; ++i) { q[i] = 0; v[i] = 0; }
         double raw[OS2R_MAX_OBS], o[OS2R_MAX_OBS];
         observe(M, T, q, v, a_old, raw, o);
-        double r = reward_fn(T, o, a, a_old);
-        int cause = is_done(T, o) ? 1 : 0;
-        int finite = 1;
-        for (int i = 0; i < n; ++i) if (!isfinite(q[i]) || !isfinite(v[i])) finite = 0;
-        if (!finite) cause |= 4;
+        double r = finite ? reward_fn(T, o, a, a_old) : 0.0;
+        int cause = (finite && is_done(T, o)) ? 1 : 0;
+        if (!finite) cause = 4;
         J->steps[e] += 1; J->ret[e] += r;
         if (T->max_episode_steps > 0 && J->steps[e] >= T->max_episode_steps) cause |= 2;
         a_prev[0] = a[0]; a_prev[1] = a[1];

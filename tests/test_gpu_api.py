@@ -100,6 +100,23 @@ def test_custom_reward_class_runs_on_device():
     ob, reward, done, _ = env.step([0.1, -0.1])
     assert reward == pytest.approx(ob[2] * 2 + 1, abs=1e-6)
     env.close()
+    # batched + auto-reset: the reward is evaluated on the pre-reset observation of every env, and the episode
+    # statistics accumulate the user's reward (the kernel itself saw reward 0)
+    N, limit = 256, 5
+    envs = make_mp_envs('Monopod-balance-v1', N, 3, randomizers.monopod_no_rand.MonopodEnvNoRandomizer,
+                        task_mode='fixed_hip', reward_class=HeightV0, max_episode_steps=limit)
+    envs.output = 'torch'
+    envs.reset()
+    total = torch.zeros(N, dtype=torch.float64, device='cuda')
+    for t in range(limit):
+        obs, rew, done, info = envs.step(torch.zeros((N, 2), device='cuda'))
+        term = info['terminal_observation']
+        assert torch.allclose(rew, (term[:, 2] * 2 + 1), atol=1e-6)
+        total += rew.double()
+    assert done.all()
+    st = envs.runtime.stats()
+    assert st['episodes'] == N and st['sum_return'] == pytest.approx(float(total.sum()), rel=1e-9)
+    envs.close()
 
 
 def test_vec_env_numpy_and_torch_paths_agree():
@@ -133,6 +150,16 @@ def test_vec_env_numpy_and_torch_paths_agree():
     assert not np.array_equal(infos[0]['terminal_observation'], obs[0]) and infos[0]['reset_orientation'] == 'stand'
     r, d = e2.get_state_info(obs, np.zeros((4, 2)))
     assert r.shape == (4,) and d.shape == (4,) and not d.any()
+    # get_attr / env_method return one entry per selected env (subproc_vec_env.py:150-175) and honour `indices`
+    assert len(e2.get_attr('action_space')) == 4 and len(e2.get_attr('action_space', indices=[0, 2])) == 2
+    assert len(e2.get_attr('action_space', indices=1)) == 1
+    assert e2.env_method('get_state_info', obs[0], [0.0, 0.0], indices=[3])[0][1] is False
+    with pytest.raises(IndexError):
+        e2.get_attr('action_space', indices=[4])
+    with pytest.raises(ValueError):
+        e2.set_attr('foo', 1, indices=[0])
+    e2.set_attr('foo', 1)
+    assert e2.runtime.foo == 1
     for e in (e_np, e_t, e2):
         e.close()
 
@@ -151,13 +178,25 @@ def test_policy_rollout_stays_on_device_and_checkpoints():
     assert torch.isfinite(obs).all() and obs.abs().max() <= 1.0
     rt = envs.runtime
     snap = rt.get_state()
+    assert {'state', 'params', 'steps', 'returns', 'reset_ids', 'episodes', 'seed', 'stats'} <= set(snap)
     with torch.no_grad():
         a = policy(obs)
         o1 = envs.step(a)[0].clone()
         rt.set_state(snap)
         o2 = envs.step(a)[0].clone()
-    done_mask = envs.runtime.engine.done_u8.bool()
-    assert torch.equal(o1[~done_mask], o2[~done_mask])
+    assert torch.equal(o1, o2)          # resets included: the episode counters (RNG streams) were restored too
+    # ... and into a NEW runtime (fresh engine): the rollout continues bit-identically
+    envs2 = make_mp_envs('Monopod-hop-v1', N, 1, randomizers.monopod.MonopodEnvRandomizer)
+    envs2.output = 'torch'
+    envs2.runtime.set_state(snap)
+    assert torch.equal(envs2.step(a)[0], o1)
+    with torch.no_grad():
+        for _ in range(5):
+            a = policy(obs)
+            obs = envs.step(a)[0]
+            assert torch.equal(envs2.step(a)[0], obs)
+    assert envs2.runtime.stats()['episodes'] == rt.stats()['episodes']
+    envs2.close()
     # ScenarIO-style pokes (examples/ignition_interaction.py)
     model = rt.task.model
     assert len(model.joint_positions(['hip_joint', 'knee_joint'])) == 2
