@@ -73,8 +73,8 @@ class TaskCfg(C.Structure):
 
 class Tuning(C.Structure):
     """struct os2r_tuning (zero = defaults)"""
-    _fields_ = [('sort_margin', _f64), ('force_block', _i32), ('force_lone', _i32), ('disable_root_fold', _i32),
-                ('force_scalar', _i32)]
+    _fields_ = [('sort_margin', _f64), ('force_block', _i32), ('force_pair', _i32), ('disable_root_fold', _i32),
+                ('_pad', _i32)]
 
 
 class PackedLayout(C.Structure):
@@ -138,7 +138,7 @@ SYMBOLS = {
     'os2r_obs_dim': (_i32, [_vp]),
     'os2r_kernel_launches': (C.c_int64, [_vp]),
     'os2r_kernel_info': (_i32, [_vp, C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32),
-                                C.POINTER(_i32), C.POINTER(_i32)]),
+                                C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32)]),
     'os2r_measure_fp32_peak': (_i32, [_i32, C.POINTER(_f64), C.POINTER(_f64)]),
 }
 

@@ -152,8 +152,8 @@ struct os2r_env {
     uint8_t *cls = nullptr;
     StatsDev *stats = nullptr;
     int sm_count = 0;
+    int build = OS2R_BUILD_F32;      // which step kernel: fp32 one env per thread (product), fp32 pairs (opt-in), fp64
     int block = OS2R_BLOCK;          // threads per block of the step kernel for this batch size
-    bool lone = false;               // at most four 2-warp blocks per SM: the build without an occupancy target
     StateDev<float> s32;
     StateDev<double> s64;
     // host staging for os2r_step_host
@@ -312,9 +312,9 @@ int set_params_impl(os2r_env *h, StateDev<T> &S, const double *in) {
 int do_step(os2r_env *h, const StepIO &io, cudaStream_t stream) {
     cudaError_t e;
     if (h->precision == 32)
-        e = launch_step<float>(h->model.n_dof, h->model.n_contacts, h->block, h->lone, h->m32, h->taskdev, h->s32, io, h->stats, stream);
+        e = launch_step<float>(h->build, h->model.n_dof, h->model.n_contacts, h->block, h->m32, h->taskdev, h->s32, io, h->stats, stream);
     else
-        e = launch_step<double>(h->model.n_dof, h->model.n_contacts, h->block, false, h->m64, h->taskdev, h->s64, io, h->stats, stream);
+        e = launch_step<double>(h->build, h->model.n_dof, h->model.n_contacts, h->block, h->m64, h->taskdev, h->s64, io, h->stats, stream);
     if (e != cudaSuccess) return fail("step kernel launch failed: %s", cudaGetErrorString(e));
     h->launches += 1;
     h->env_steps += (uint64_t)h->n;
@@ -367,12 +367,10 @@ int32_t os2r_create_tuned(const os2r_model *model, const os2r_task_cfg *task, in
 
     os2r_env *h = new os2r_env();
     h->sm_count = sm_count;
-    h->block = precision == 32 ? step_block_threads<float>(n_envs, sm_count) : step_block_threads<double>(n_envs, sm_count);
+    h->build = precision == 64 ? OS2R_BUILD_F64 : (tune.force_pair ? OS2R_BUILD_PAIR : OS2R_BUILD_F32);
+    h->block = step_block_threads(h->build, n_envs, sm_count);
     if (tune.force_block == OS2R_BLOCK || (precision == 32 && tune.force_block == OS2R_BLOCK_WIDE)) h->block = tune.force_block;
-    else if (tune.force_block != 0) { delete h; return fail("os2r_create: tuning.force_block %d unsupported (%d or %d)", tune.force_block, OS2R_BLOCK, OS2R_BLOCK_WIDE); }
-    // up to four 2-warp blocks per SM fit at ~225 registers per thread: every batch that runs on the narrow blocks
-    h->lone = precision == 32 && h->block == OS2R_BLOCK && n_envs <= (int64_t)sm_count * 4 * OS2R_BLOCK;
-    if (tune.force_lone != 0 && precision == 32 && h->block == OS2R_BLOCK) h->lone = tune.force_lone > 0;
+    else if (tune.force_block != 0) { delete h; return fail("os2r_create: tuning.force_block %d unsupported (%d, or %d for the fp32 builds)", tune.force_block, OS2R_BLOCK, OS2R_BLOCK_WIDE); }
     h->model = *model; h->task = *task; h->precision = precision; h->device = device;
     h->n = n_envs; h->first_env_id = first_env_id; h->seed = seed;
     h->rows = model->n_dof + 3 * model->n_contacts;
@@ -401,7 +399,7 @@ int32_t os2r_create_tuned(const os2r_model *model, const os2r_task_cfg *task, in
     if ((e = cudaMalloc(&h->cls, n_envs)) != cudaSuccess) return cleanup("cudaMalloc(cls)", e);
     if ((e = cudaMalloc(&h->stats, sizeof(StatsDev))) != cudaSuccess) return cleanup("cudaMalloc(stats)", e);
     if ((e = cudaMemset(h->stats, 0, sizeof(StatsDev))) != cudaSuccess) return cleanup("cudaMemset(stats)", e);
-    e = precision == 32 ? prepare_step<float>(model->n_dof, h->block) : prepare_step<double>(model->n_dof, h->block);
+    e = prepare_step(h->build, model->n_dof, h->block);
     if (e != cudaSuccess) return cleanup("cudaFuncSetAttribute(step kernel shared memory)", e);
     if (precision == 32) { carve<float>(h, h->s32); e = launch_init<float>(h->taskdev, h->s32, model->gravity_z, 0); }
     else { carve<double>(h, h->s64); e = launch_init<double>(h->taskdev, h->s64, model->gravity_z, 0); }
@@ -714,16 +712,16 @@ int32_t os2r_obs_dim(const os2r_env *h) { return h ? h->task.obs_dim : 0; }
 int64_t os2r_kernel_launches(const os2r_env *h) { return h ? h->launches : 0; }
 
 int32_t os2r_kernel_info(const os2r_env *h, int32_t *block_threads, int32_t *grid_blocks, int32_t *regs_per_thread,
-                         int32_t *local_bytes_per_thread, int32_t *resident_blocks_per_sm) {
+                         int32_t *local_bytes_per_thread, int32_t *resident_blocks_per_sm, int32_t *envs_per_thread) {
     if (!h) return fail("os2r_kernel_info: null handle");
     DeviceGuard guard(h->device);
     cudaFuncAttributes a;
-    int resident = 0;
-    cudaError_t e = h->precision == 32 ? step_kernel_attributes<float>(h->model.n_dof, h->block, h->m32.any_damping != 0, &a, &resident)
-                                       : step_kernel_attributes<double>(h->model.n_dof, h->block, true, &a, &resident);
+    int resident = 0, epb = h->block;
+    cudaError_t e = step_kernel_attributes(h->build, h->model.n_dof, h->block, h->m32.any_damping != 0, &a, &resident, &epb);
     if (e != cudaSuccess) return fail("cudaFuncGetAttributes failed: %s", cudaGetErrorString(e));
     if (block_threads) *block_threads = h->block;
-    if (grid_blocks) *grid_blocks = (int32_t)((h->n + h->block - 1) / h->block);
+    if (grid_blocks) *grid_blocks = (int32_t)((h->n + epb - 1) / epb);
+    if (envs_per_thread) *envs_per_thread = epb / h->block;
     if (regs_per_thread) *regs_per_thread = a.numRegs;
     if (local_bytes_per_thread) *local_bytes_per_thread = (int32_t)a.localSizeBytes;
     if (resident_blocks_per_sm) *resident_blocks_per_sm = resident;

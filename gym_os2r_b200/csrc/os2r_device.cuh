@@ -111,10 +111,54 @@ struct StatsDev {                // device-side accumulators (os2r_stats without
 };
 
 // ------------------------------------------------------------------------------------------------
-// scalar helpers
+// value types: the physics is written once over a value type V
+//   float / double : one env per thread (double = the verification build)
+//   f2             : TWO envs per thread in one 64-bit register pair, arithmetic through the packed fp32x2
+//                    instructions of sm_100 (PTX fma/add/sub/mul.rn.f32x2 -> SASS FFMA2 / FADD2 / FMUL2). One FFMA2
+//                    issues in ONE scheduler slot and does the work of two FFMAs (measured on B200,
+//                    tools/microbench/ffma2_probe.cu: same 4.6-cycle dependent latency as FFMA, two FMA-pipe cycles per
+//                    warp instruction, i.e. the same peak flops through HALF the issue slots). The step kernel is
+//                    issue- and latency-bound, not FMA-pipe-bound, so the pair build is the
+//                    product path for fp32. Scalars (model constants in the constant bank, immediates) broadcast to both
+//                    halves inside the instruction (`R.F32` / `UR.F32` operand forms): no duplication needed.
+// Per-half operations without a packed instruction (min / max / compare / select / MUFU) run once per half.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void sincos_t(float x, float *s, float *c) { sincosf(x, s, c); }
-__device__ __forceinline__ void sincos_t(double x, double *s, double *c) { sincos(x, s, c); }
+struct f2 {
+    unsigned long long r;
+    __device__ __forceinline__ f2() {}
+    __device__ __forceinline__ f2(float s) { asm("mov.b64 %0, {%1, %1};" : "=l"(r) : "f"(s)); }
+    __device__ __forceinline__ f2(float lo, float hi) { asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); }
+    __device__ __forceinline__ float lo() const { float a; asm("{ .reg .f32 t; mov.b64 {%0, t}, %1; }" : "=f"(a) : "l"(r)); return a; }
+    __device__ __forceinline__ float hi() const { float b; asm("{ .reg .f32 t; mov.b64 {t, %0}, %1; }" : "=f"(b) : "l"(r)); return b; }
+};
+__device__ __forceinline__ f2 operator+(f2 a, f2 b) { f2 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d.r) : "l"(a.r), "l"(b.r)); return d; }
+__device__ __forceinline__ f2 operator-(f2 a, f2 b) { f2 d; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d.r) : "l"(a.r), "l"(b.r)); return d; }
+__device__ __forceinline__ f2 operator*(f2 a, f2 b) { f2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d.r) : "l"(a.r), "l"(b.r)); return d; }
+__device__ __forceinline__ f2 operator-(f2 a) { return f2(-a.lo(), -a.hi()); }   // folds into the consumer's operand modifier
+__device__ __forceinline__ f2 &operator+=(f2 &a, f2 b) { a = a + b; return a; }
+__device__ __forceinline__ f2 &operator-=(f2 &a, f2 b) { a = a - b; return a; }
+__device__ __forceinline__ f2 &operator*=(f2 &a, f2 b) { a = a * b; return a; }
+
+template <typename V> struct VT;             // traits: scalar type, envs per thread, mask type
+template <> struct VT<float>  { using S = float;  using M = bool; static constexpr int LANES = 1; };
+template <> struct VT<double> { using S = double; using M = bool; static constexpr int LANES = 1; };
+struct m2 { bool a, b; };
+template <> struct VT<f2>     { using S = float;  using M = m2;   static constexpr int LANES = 2; };
+
+// half h of a value (h is a compile-time constant at every call site)
+__device__ __forceinline__ float half_of(float v, int) { return v; }
+__device__ __forceinline__ double half_of(double v, int) { return v; }
+__device__ __forceinline__ float half_of(f2 v, int h) { return h ? v.hi() : v.lo(); }
+
+__device__ __forceinline__ float fma_t(float a, float b, float c) { return fmaf(a, b, c); }
+__device__ __forceinline__ double fma_t(double a, double b, double c) { return fma(a, b, c); }
+__device__ __forceinline__ f2 fma_t(f2 a, f2 b, f2 c) { f2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d.r) : "l"(a.r), "l"(b.r), "l"(c.r)); return d; }
+__device__ __forceinline__ float fmin_t(float a, float b) { return fminf(a, b); }
+__device__ __forceinline__ double fmin_t(double a, double b) { return fmin(a, b); }
+__device__ __forceinline__ f2 fmin_t(f2 a, f2 b) { return f2(fminf(a.lo(), b.lo()), fminf(a.hi(), b.hi())); }
+__device__ __forceinline__ float fmax_t(float a, float b) { return fmaxf(a, b); }
+__device__ __forceinline__ double fmax_t(double a, double b) { return fmax(a, b); }
+__device__ __forceinline__ f2 fmax_t(f2 a, f2 b) { return f2(fmaxf(a.lo(), b.lo()), fmaxf(a.hi(), b.hi())); }
 __device__ __forceinline__ float sqrt_t(float x) { return sqrtf(x); }
 __device__ __forceinline__ double sqrt_t(double x) { return sqrt(x); }
 // 1/sqrt(x) to ~1 ulp: MUFU.RSQ + one Newton step (shorter dependency chain than sqrtf followed by a division)
@@ -123,6 +167,10 @@ __device__ __forceinline__ float rsqrt_t(float x) {
     return fmaf(r, fmaf(-0.5f * x * r, r, 0.5f), r);
 }
 __device__ __forceinline__ double rsqrt_t(double x) { return 1.0 / sqrt(x); }
+__device__ __forceinline__ f2 rsqrt_t(f2 x) {   // same operations per half as the scalar routine, Newton step packed
+    const f2 r(rsqrtf(x.lo()), rsqrtf(x.hi()));
+    return fma_t(r, fma_t(f2(-0.5f) * x * r, r, f2(0.5f)), r);
+}
 // MUFU.RCP (~1 ulp), no IEEE fix-up / denormal slow path: only used for the row relaxation factors 1/(A(1+cfm)),
 // whose rounding moves the sweep's fixed point by cfm * ulp (the fixed point itself does not depend on the factor)
 __device__ __forceinline__ float rcp_t(float x) {
@@ -131,55 +179,90 @@ __device__ __forceinline__ float rcp_t(float x) {
     return r;
 }
 __device__ __forceinline__ double rcp_t(double x) { return 1.0 / x; }
-__device__ __forceinline__ float fma_t(float a, float b, float c) { return fmaf(a, b, c); }
-__device__ __forceinline__ double fma_t(double a, double b, double c) { return fma(a, b, c); }
-__device__ __forceinline__ float fmin_t(float a, float b) { return fminf(a, b); }
-__device__ __forceinline__ double fmin_t(double a, double b) { return fmin(a, b); }
-__device__ __forceinline__ float fmax_t(float a, float b) { return fmaxf(a, b); }
-__device__ __forceinline__ double fmax_t(double a, double b) { return fmax(a, b); }
+__device__ __forceinline__ f2 rcp_t(f2 x) { return f2(rcp_t(x.lo()), rcp_t(x.hi())); }
+
+// masks: per-env predicates (a pair build carries one per half)
+__device__ __forceinline__ bool gt_t(float a, float b) { return a > b; }
+__device__ __forceinline__ bool gt_t(double a, double b) { return a > b; }
+__device__ __forceinline__ m2 gt_t(f2 a, f2 b) { return m2{a.lo() > b.lo(), a.hi() > b.hi()}; }
+__device__ __forceinline__ bool le_t(float a, float b) { return a <= b; }
+__device__ __forceinline__ bool le_t(double a, double b) { return a <= b; }
+__device__ __forceinline__ m2 le_t(f2 a, f2 b) { return m2{a.lo() <= b.lo(), a.hi() <= b.hi()}; }
+__device__ __forceinline__ bool any_t(bool m) { return m; }
+__device__ __forceinline__ bool any_t(m2 m) { return m.a || m.b; }
+__device__ __forceinline__ bool and_not(bool m, bool k) { return m && !k; }
+__device__ __forceinline__ m2 and_not(m2 m, m2 k) { return m2{m.a && !k.a, m.b && !k.b}; }
+__device__ __forceinline__ float sel_t(bool m, float a, float b) { return m ? a : b; }
+__device__ __forceinline__ double sel_t(bool m, double a, double b) { return m ? a : b; }
+__device__ __forceinline__ f2 sel_t(m2 m, f2 a, f2 b) { return f2(m.a ? a.lo() : b.lo(), m.b ? a.hi() : b.hi()); }
+template <typename V> __device__ __forceinline__ typename VT<V>::M all_true();
+template <> __device__ __forceinline__ bool all_true<float>() { return true; }
+template <> __device__ __forceinline__ bool all_true<double>() { return true; }
+template <> __device__ __forceinline__ m2 all_true<f2>() { return m2{true, true}; }
 
 // sin / cos of a compensated angle hi + lo: sin(hi+lo) = s + lo*c, cos(hi+lo) = c - lo*s.
-// Deliberately NOT inlined: sincosf's range-reduction slow path is ~150 instructions, and the physics loop
-// calls this once per joint; one shared copy keeps the loop body inside the instruction cache.
 template <typename T>
 struct SinCos { T s, c; };       // returned by value: stays in registers across the call (pointers would go via the stack)
-// fp32 sin/cos for the forward pass, inlined and evaluated for all joints of an env side by side (independent
-// chains the compiler interleaves; the out-of-line sincosf call per joint was 7 % of the instructions but 13 % of the
-// stall samples of the contact-free step: call overhead, one chain at a time, and its far-away code was refetched
-// by every call). Three-term Cody-Waite reduction by pi/2 (the same scheme as the library's fast path, exact enough for
-// |x| < 1e5; beyond that the library routine is called) and the cephes minimax polynomials on [-pi/4, pi/4]: <= 1 ulp.
-__device__ __forceinline__ void sincos_fast(float x, float *sn, float *cs) {
-    const float j = rintf(x * 0.636619772367581343f);          // x * 2/pi
-    float r = fmaf(j, -1.57079601287841796875f, x);            // pi/2 split in three parts
-    r = fmaf(j, -3.1391647326017846353352069854736328125e-7f, r);
-    r = fmaf(j, -5.390302529957764765544681040410068817436695098876953125e-15f, r);
-    const int q = (int)j;
-    const float r2 = r * r;
-    float ps = fmaf(r2, -1.9515295891e-4f, 8.3321608736e-3f);
-    ps = fmaf(ps, r2, -1.6666654611e-1f);
-    const float sr = fmaf(ps * r2, r, r);                      // sin r
-    float pc = fmaf(r2, 2.443315711809948e-5f, -1.388731625493765e-3f);
-    pc = fmaf(pc, r2, 4.166664568298827e-2f);
-    const float cr = fmaf(pc * r2, r2, fmaf(r2, -0.5f, 1.0f)); // cos r
-    const float s0 = (q & 1) ? cr : sr, c0 = (q & 1) ? sr : cr;
-    *sn = (q & 2) ? -s0 : s0;
-    *cs = ((q + 1) & 2) ? -c0 : c0;
-}
-
+__device__ __forceinline__ void sincos_t(float x, float *s, float *c) { sincosf(x, s, c); }
+__device__ __forceinline__ void sincos_t(double x, double *s, double *c) { sincos(x, s, c); }
+// Library routine, deliberately NOT inlined (its range-reduction slow path is ~150 instructions): the fp32 builds only
+// reach it beyond 1e5 rad, the fp64 build calls it once per joint.
 template <typename T>
 __device__ __noinline__ SinCos<T> joint_sincos(T hi, T lo) {
     T s, c;
     sincos_t(hi, &s, &c);
     return SinCos<T>{s + lo * c, c - lo * s};
 }
+// fp32 sin/cos for the forward pass, inlined and evaluated for all joints of an env side by side (independent
+// chains the compiler interleaves; an out-of-line sincosf call per joint was 7 % of the instructions but 13 % of the
+// stall samples of the contact-free step). Three-term Cody-Waite reduction by pi/2 (the same scheme as the library's
+// fast path, exact enough for |x| < 1e5; beyond that the library routine is called) and the cephes minimax
+// polynomials on [-pi/4, pi/4]: <= 1 ulp. Written over V so that the pair build runs reduction and polynomials packed;
+// only the rounding to the quadrant and the quadrant selection run per half.
+__device__ __forceinline__ float rint_t(float x) { return rintf(x); }
+__device__ __forceinline__ f2 rint_t(f2 x) { return f2(rintf(x.lo()), rintf(x.hi())); }
+__device__ __forceinline__ void quadrant_fix(float j, float sr, float cr, float *sn, float *cs) {
+    const int q = (int)j;
+    const float s0 = (q & 1) ? cr : sr, c0 = (q & 1) ? sr : cr;
+    *sn = (q & 2) ? -s0 : s0;
+    *cs = ((q + 1) & 2) ? -c0 : c0;
+}
+__device__ __forceinline__ void quadrant_fix(f2 j, f2 sr, f2 cr, f2 *sn, f2 *cs) {
+    float s0, c0, s1, c1;
+    quadrant_fix(j.lo(), sr.lo(), cr.lo(), &s0, &c0);
+    quadrant_fix(j.hi(), sr.hi(), cr.hi(), &s1, &c1);
+    *sn = f2(s0, s1);
+    *cs = f2(c0, c1);
+}
+template <typename V>
+__device__ __forceinline__ void sincos_fast(V x, V *sn, V *cs) {
+    const V j = rint_t(x * V(0.636619772367581343f));          // x * 2/pi
+    V r = fma_t(j, V(-1.57079601287841796875f), x);            // pi/2 split in three parts
+    r = fma_t(j, V(-3.1391647326017846353352069854736328125e-7f), r);
+    r = fma_t(j, V(-5.390302529957764765544681040410068817436695098876953125e-15f), r);
+    const V r2 = r * r;
+    V ps = fma_t(r2, V(-1.9515295891e-4f), V(8.3321608736e-3f));
+    ps = fma_t(ps, r2, V(-1.6666654611e-1f));
+    const V sr = fma_t(ps * r2, r, r);                         // sin r
+    V pc = fma_t(r2, V(2.443315711809948e-5f), V(-1.388731625493765e-3f));
+    pc = fma_t(pc, r2, V(4.166664568298827e-2f));
+    const V cr = fma_t(pc * r2, r2, fma_t(r2, V(-0.5f), V(1.0f))); // cos r
+    quadrant_fix(j, sr, cr, sn, cs);
+}
+// all joint angles of the thread's env(s): sin / cos of hi + lo
+__device__ __forceinline__ bool beyond_fast_range(float q) { return !(fabsf(q) < 1.0e5f); }
+__device__ __forceinline__ bool beyond_fast_range(f2 q) { return !(fabsf(q.lo()) < 1.0e5f) || !(fabsf(q.hi()) < 1.0e5f); }
+__device__ __forceinline__ SinCos<float> slow_sincos(float hi, float lo) { return joint_sincos<float>(hi, lo); }
+__device__ __forceinline__ SinCos<f2> slow_sincos(f2 hi, f2 lo) {
+    const SinCos<float> a = joint_sincos<float>(hi.lo(), lo.lo()), b = joint_sincos<float>(hi.hi(), lo.hi());
+    return SinCos<f2>{f2(a.s, b.s), f2(a.c, b.c)};
+}
 
-// bit-preserving int <-> T for parking integers in the T-typed shared-memory slots
-template <typename T> __device__ __forceinline__ T __int_as_float_t(int v);
-template <> __device__ __forceinline__ float __int_as_float_t<float>(int v) { return __int_as_float(v); }
-template <> __device__ __forceinline__ double __int_as_float_t<double>(int v) { return __hiloint2double(0, v); }
-template <typename T> __device__ __forceinline__ int __float_as_int_t(T v);
-template <> __device__ __forceinline__ int __float_as_int_t<float>(float v) { return __float_as_int(v); }
-template <> __device__ __forceinline__ int __float_as_int_t<double>(double v) { return __double2loint(v); }
+// bit-preserving int <-> float for parking integers in the shared-memory slots
+__device__ __forceinline__ float int_as_real(float, int v) { return __int_as_float(v); }
+__device__ __forceinline__ double int_as_real(double, int v) { return __hiloint2double(0, v); }
+__device__ __forceinline__ int real_as_int(float v) { return __float_as_int(v); }
+__device__ __forceinline__ int real_as_int(double v) { return __double2loint(v); }
 
 #define OS2R_CROSS(o, a, b)                    \
     do {                                       \
@@ -252,7 +335,8 @@ enum { DRAW_RESET = 0, DRAW_PITCH = 1, DRAW_NOISE = 2, DRAW_LAYSIDE = 4, DRAW_DI
 // Per-thread data that is touched only a few times per physics iteration lives in shared memory,
 // laid out [slot][thread] (bank = thread, conflict-free): warm-start impulses, randomised parameters,
 // the compensation terms of the (hi, lo) state pairs, torques and the contact-sphere centres.
-// Only what every phase needs (q_hi, v, gravity) stays in registers.
+// Only what every phase needs (q_hi, v, gravity) stays in registers. A slot holds one V: a float / double, or in the
+// pair build the f2 of the thread's two envs (8-byte accesses, half h of slot k is the float at byte offset 4h).
 template <int N, int NC>
 struct ColdSlots {
     static constexpr int ROWS = N + 3 * NC;
@@ -265,26 +349,34 @@ struct ColdSlots {
     static constexpr int QLO = TAU + N;           // [N]
     static constexpr int VLO = QLO + N;           // [N]
     static constexpr int CX = VLO + N;            // [3*NC] contact centres (world)
-    static constexpr int AOLD = CX + 3 * NC;      // [2] previous action (loaded in the prologue, used by the epilogue)
-    static constexpr int MISC = AOLD + 2;         // [3] episode step counter, episode return (lo, hi words)
-    static constexpr int COUNT = MISC + 3;
+    static constexpr int ACT = CX + 3 * NC;       // [2] this step's clamped action (0 when it was not finite)
+    static constexpr int AFIN = ACT + 2;          // [1] 1 = the action was finite
+    static constexpr int QHI = AFIN + 1;          // [N] q_hi, v parked after the last iteration: the fp64 epilogue runs
+    static constexpr int VHI = QHI + N;           // [N]   once per env and reads everything per half from here
+    static constexpr int COUNT = VHI + N;
 };
 
-template <typename T, int STRIDE>
+template <typename V, int STRIDE>
 struct Cold {                    // accessor: slot k of this thread (STRIDE = threads per block, compile time so
-    T *base;                     // that every access is base + immediate offset; base = &smem[threadIdx.x])
-    __device__ __forceinline__ T &operator()(int k) const { return base[k * STRIDE]; }
+    V *base;                     // that every access is base + immediate offset; base = &smem[threadIdx.x])
+    using S = typename VT<V>::S;
+    __device__ __forceinline__ V &operator()(int k) const { return base[k * STRIDE]; }
+    // half h of slot k as a scalar (the epilogue's view: one env at a time)
+    __device__ __forceinline__ S &half(int k, int h) const { return reinterpret_cast<S *>(base + k * STRIDE)[h]; }
 };
 
-template <typename T, int N>
+template <typename V, int N>
 struct EnvRegs {                 // hot per-thread state
-    T q_hi[N], v[N];
-    T gz;                        // gravity z (negative)
+    V q_hi[N], v[N];
+    V gz;                        // gravity z (negative)
 };
 
-template <typename T, int N, int NC, bool DAMPED, typename ColdT>
-__device__ __forceinline__ void physics_iteration(const ModelDev<T> &M, EnvRegs<T, N> &E, const ColdT &C) {
+template <typename V, int N, int NC, bool DAMPED, typename ColdT>
+__device__ __forceinline__ void physics_iteration(const ModelDev<typename VT<V>::S> &M, EnvRegs<V, N> &E, const ColdT &C) {
     using SL = ColdSlots<N, NC>;
+    using T = typename VT<V>::S;
+    using Mask = typename VT<V>::M;
+    constexpr bool FP32 = sizeof(T) == 4;
     const T dt = M.dt;
 
     // ---- single forward pass: kinematics, velocities, and direct accumulation of the joint-space mass
@@ -292,59 +384,59 @@ __device__ __forceinline__ void physics_iteration(const ModelDev<T> &M, EnvRegs<
     //      (classical world-frame Newton-Euler with qdd = 0; gravity as an upward base acceleration).
     //      Every term is a difference of nearby points or a positive contribution: no reference point,
     //      no m|r|^2 cancellation, and nothing per-body has to be kept for a backward pass.
-    T ax[N][3];      // joint axes, world
-    T P[N][3];       // joint origins, world
-    T Mm[N][N];      // lower triangle (Mm[j][k], k <= j)
-    T hb[N];         // bias forces
+    V ax[N][3];      // joint axes, world
+    V P[N][3];       // joint origins, world
+    V Mm[N][N];      // lower triangle (Mm[j][k], k <= j)
+    V hb[N];         // bias forces
 #pragma unroll
     for (int j = 0; j < N; ++j) {
-        hb[j] = 0;
+        hb[j] = V(0);
 #pragma unroll
-        for (int k = 0; k <= j; ++k) Mm[j][k] = 0;
+        for (int k = 0; k <= j; ++k) Mm[j][k] = V(0);
     }
-    T sn[N], cs[N];      // sin / cos of every joint angle (hi + lo)
-    if (sizeof(T) == 4) {
+    V sn[N], cs[N];      // sin / cos of every joint angle (hi + lo)
+    if constexpr (FP32) {
         bool big = false;
 #pragma unroll
-        for (int i = 0; i < N; ++i) big = big || !(fabsf((float)E.q_hi[i]) < 1.0e5f);
+        for (int i = 0; i < N; ++i) big = big || beyond_fast_range(E.q_hi[i]);
         if (big) {       // a joint that has turned > 15 000 revolutions (or is non-finite): library range reduction
 #pragma unroll
             for (int i = 0; i < N; ++i) {
-                const SinCos<T> sc = joint_sincos<T>(E.q_hi[i], C(SL::QLO + i));
+                const SinCos<V> sc = slow_sincos(E.q_hi[i], C(SL::QLO + i));
                 sn[i] = sc.s; cs[i] = sc.c;
             }
         } else {
 #pragma unroll
             for (int i = 0; i < N; ++i) {
-                float s, c;
-                sincos_fast((float)E.q_hi[i], &s, &c);
-                const T lo = C(SL::QLO + i);
-                sn[i] = (T)s + lo * (T)c;
-                cs[i] = (T)c - lo * (T)s;
+                V s, c;
+                sincos_fast<V>(E.q_hi[i], &s, &c);
+                const V lo = C(SL::QLO + i);
+                sn[i] = s + lo * c;
+                cs[i] = c - lo * s;
             }
         }
     } else {
 #pragma unroll
         for (int i = 0; i < N; ++i) {
-            const SinCos<T> sc = joint_sincos<T>(E.q_hi[i], T(0));
+            const SinCos<V> sc = joint_sincos<V>(E.q_hi[i], V(0));
             sn[i] = sc.s; cs[i] = sc.c;
         }
     }
     {
-        T R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
-        T p[3] = {0, 0, 0};
-        T w[3] = {0, 0, 0}, al[3] = {0, 0, 0}, ap[3] = {0, 0, -E.gz};   // ang. vel, ang. acc, acc of joint origin
+        V R[9] = {V(1), V(0), V(0), V(0), V(1), V(0), V(0), V(0), V(1)};
+        V p[3] = {V(0), V(0), V(0)};
+        V w[3] = {V(0), V(0), V(0)}, al[3] = {V(0), V(0), V(0)}, ap[3] = {V(0), V(0), -E.gz};   // ang. vel, ang. acc, acc of joint origin
 #pragma unroll
         for (int i = 0; i < N; ++i) {
-            T A[9];
+            V A[9];
             if (i == 0) {
 #pragma unroll
-                for (int k = 0; k < 3; ++k) p[k] = M.tree_p[0][k];
+                for (int k = 0; k < 3; ++k) p[k] = V(M.tree_p[0][k]);
 #pragma unroll
-                for (int k = 0; k < 9; ++k) A[k] = M.tree_R[0][k];
+                for (int k = 0; k < 9; ++k) A[k] = V(M.tree_R[0][k]);
             } else {
                 const T *tp = M.tree_p[i];
-                T dp[3], wd[3];
+                V dp[3], wd[3];
 #pragma unroll
                 for (int r = 0; r < 3; ++r) dp[r] = R[3 * r] * tp[0] + R[3 * r + 1] * tp[1] + R[3 * r + 2] * tp[2];
                 // acceleration of the next joint origin, carried by the parent body: ap += al x dp + w x (w x dp)
@@ -360,19 +452,19 @@ __device__ __forceinline__ void physics_iteration(const ModelDev<T> &M, EnvRegs<
                     for (int c = 0; c < 3; ++c)
                         A[3 * r + c] = R[3 * r] * tR[c] + R[3 * r + 1] * tR[3 + c] + R[3 * r + 2] * tR[6 + c];
             }
-            const T s = sn[i], c = cs[i];
+            const V s = sn[i], c = cs[i];
 #pragma unroll
             for (int r = 0; r < 3; ++r) {
-                const T a1 = A[3 * r + 1], a2 = A[3 * r + 2];
+                const V a1 = A[3 * r + 1], a2 = A[3 * r + 2];
                 R[3 * r] = A[3 * r];
                 R[3 * r + 1] = c * a1 + s * a2;
                 R[3 * r + 2] = c * a2 - s * a1;
                 ax[i][r] = A[3 * r];
                 P[i][r] = p[r];
             }
-            const T qd = E.v[i];
+            const V qd = E.v[i];
             if (i > 0) {   // al += (w_parent x a_i) qd
-                T wa[3];
+                V wa[3];
                 OS2R_CROSS(wa, w, ax[i]);
 #pragma unroll
                 for (int r = 0; r < 3; ++r) al[r] += wa[r] * qd;
@@ -380,17 +472,17 @@ __device__ __forceinline__ void physics_iteration(const ModelDev<T> &M, EnvRegs<
 #pragma unroll
             for (int r = 0; r < 3; ++r) w[r] += ax[i][r] * qd;
             if (i == 0 && M.root_spin) {   // warp-uniform; ~130 instructions of body 0 become one FMA
-                Mm[0][0] = fma_t(M.root_mass_term, C(SL::MASS), M.root_inertia_term);
+                Mm[0][0] = fma_t(V(M.root_mass_term), C(SL::MASS), V(M.root_inertia_term));
             } else {
             // COM offset and rotational inertia in world axes
             const T *cm = M.com[i];
-            T d[3];
+            V d[3];
 #pragma unroll
             for (int r = 0; r < 3; ++r) d[r] = R[3 * r] * cm[0] + R[3 * r + 1] * cm[1] + R[3 * r + 2] * cm[2];
-            T Iw[6];
+            V Iw[6];
             {
                 const T *Ib = M.inertia[i];
-                T t[9];
+                V t[9];
 #pragma unroll
                 for (int r = 0; r < 3; ++r) {
                     t[3 * r + 0] = R[3 * r] * Ib[0] + R[3 * r + 1] * Ib[3] + R[3 * r + 2] * Ib[4];
@@ -404,9 +496,9 @@ __device__ __forceinline__ void physics_iteration(const ModelDev<T> &M, EnvRegs<
                 Iw[4] = t[0] * R[6] + t[1] * R[7] + t[2] * R[8];
                 Iw[5] = t[3] * R[6] + t[4] * R[7] + t[5] * R[8];
             }
-            const T m = M.mass[i] * C(SL::MASS + i);
+            const V m = C(SL::MASS + i) * M.mass[i];
             // body wrench about its COM (qdd = 0): f = m (ap + al x d + w x (w x d)), n = Iw al + w x (Iw w)
-            T f[3], nn[3], wd[3], Iwv[3];
+            V f[3], nn[3], wd[3], Iwv[3];
             OS2R_CROSS(wd, w, d);
 #pragma unroll
             for (int r = 0; r < 3; ++r) f[r] = ap[r];
@@ -418,10 +510,10 @@ __device__ __forceinline__ void physics_iteration(const ModelDev<T> &M, EnvRegs<
             OS2R_SYMV(nn, Iw, al);
             OS2R_CROSS_ACC(nn, w, Iwv);
             // joint-space accumulation over this body's ancestors j <= i
-            T Jv[N][3], u[N][3];
+            V Jv[N][3], u[N][3];
 #pragma unroll
             for (int j = 0; j <= i; ++j) {
-                const T rr[3] = {p[0] + d[0] - P[j][0], p[1] + d[1] - P[j][1], p[2] + d[2] - P[j][2]};
+                const V rr[3] = {p[0] + d[0] - P[j][0], p[1] + d[1] - P[j][1], p[2] + d[2] - P[j][2]};
                 OS2R_CROSS(Jv[j], ax[j], rr);
                 OS2R_SYMV(u[j], Iw, ax[j]);
                 OS2R_DOT_ACC(hb[j], Jv[j], f);
@@ -447,57 +539,57 @@ __device__ __forceinline__ void physics_iteration(const ModelDev<T> &M, EnvRegs<
     }
     __syncthreads();   // second phase-alignment point per iteration (see the note at the physics loop)
     // ---- Cholesky of M (and of M + dt*D when any joint is damped); qdd; v* = v + dt*qdd ------------------
-    T L[N][N];       // Cholesky factor of the plain M (lower); Ld = reciprocal diagonal
-    T Ld[N];
-    T vs[N], dvq[N];
-    auto cholesky = [&](const T *dadd, T(&Lo)[N][N], T(&Lrd)[N]) {
+    V L[N][N];       // Cholesky factor of the plain M (lower); Ld = reciprocal diagonal
+    V Ld[N];
+    V vs[N], dvq[N];
+    auto cholesky = [&](const V *dadd, V(&Lo)[N][N], V(&Lrd)[N]) {
 #pragma unroll
         for (int j = 0; j < N; ++j) {
-            T d = Mm[j][j] + dadd[j];
+            V d = Mm[j][j] + dadd[j];
 #pragma unroll
             for (int k = 0; k < j; ++k) d -= Lo[j][k] * Lo[j][k];
-            const T rd = rsqrt_t(d);
+            const V rd = rsqrt_t(d);
             Lo[j][j] = d * rd;
             Lrd[j] = rd;
 #pragma unroll
             for (int i = j + 1; i < N; ++i) {
-                T s = Mm[i][j];
+                V s = Mm[i][j];
 #pragma unroll
                 for (int k = 0; k < j; ++k) s -= Lo[i][k] * Lo[j][k];
                 Lo[i][j] = s * rd;
             }
         }
     };
-    auto solve = [&](const T(&Lo)[N][N], const T(&Lrd)[N], const T *b, T *x) {
-        T y[N];
+    auto solve = [&](const V(&Lo)[N][N], const V(&Lrd)[N], const V *b, V *x) {
+        V y[N];
 #pragma unroll
         for (int i = 0; i < N; ++i) {
-            T s = b[i];
+            V s = b[i];
 #pragma unroll
             for (int k = 0; k < i; ++k) s -= Lo[i][k] * y[k];
             y[i] = s * Lrd[i];
         }
 #pragma unroll
         for (int i = N - 1; i >= 0; --i) {
-            T s = y[i];
+            V s = y[i];
 #pragma unroll
             for (int k = i + 1; k < N; ++k) s -= Lo[k][i] * x[k];
             x[i] = s * Lrd[i];
         }
     };
     {
-        T rhs[N], zero[N];
+        V rhs[N], zero[N];
 #pragma unroll
         for (int i = 0; i < N; ++i) {
-            zero[i] = 0;
+            zero[i] = V(0);
             rhs[i] = C(SL::TAU + i) - C(SL::DAMP + i) * E.v[i] - hb[i];
         }
         cholesky(zero, L, Ld);
-        T qdd[N];
+        V qdd[N];
         if (DAMPED) {   // compile-time: the second factorisation is ~1.6 KB of loop body the undamped models never run
-            T dd[N], L2[N][N], L2d[N];
+            V dd[N], L2[N][N], L2d[N];
 #pragma unroll
-            for (int i = 0; i < N; ++i) dd[i] = dt * C(SL::DAMP + i);
+            for (int i = 0; i < N; ++i) dd[i] = C(SL::DAMP + i) * dt;
             cholesky(dd, L2, L2d);
             solve(L2, L2d, rhs, qdd);
         } else {
@@ -505,31 +597,30 @@ __device__ __forceinline__ void physics_iteration(const ModelDev<T> &M, EnvRegs<
         }
 #pragma unroll
         for (int i = 0; i < N; ++i) {
-            dvq[i] = dt * qdd[i];
+            dvq[i] = qdd[i] * dt;
             vs[i] = E.v[i] + dvq[i];
         }
     }
     // whitened velocity z0 = L^T v*. The solver tracks only the impulse-induced change z (total = z0 + z):
     // v_new = v* + L^-T z, so the (usually tiny) constraint correction never round-trips v through L.
-    T z0[N], z[N];
+    V z0[N], z[N];
 #pragma unroll
     for (int i = 0; i < N; ++i) {
-        T s = 0;
+        V s = V(0);
 #pragma unroll
         for (int k = i; k < N; ++k) s += L[k][i] * vs[k];
         z0[i] = s;
-        z[i] = 0;
+        z[i] = V(0);
     }
     // ---- constraint rows in whitened coordinates: G_r = L^-1 J_r^T ----------------------------------------
-    T Gj[N][N];      // joint friction row r: column r of L^-1 (entries k >= r)
-    T Aj[N], bj[N];  // reciprocal regularised diagonal; row velocity before impulses
-    bool jact[N];
+    V Gj[N][N];      // joint friction row r: column r of L^-1 (entries k >= r)
+    V Aj[N], bj[N];  // reciprocal regularised diagonal; row velocity before impulses
 #pragma unroll
     for (int r = 0; r < N; ++r) {
-        T a = 0, b = 0;
+        V a = V(0), b = V(0);
 #pragma unroll
         for (int k = r; k < N; ++k) {
-            T s = (k == r) ? T(1) : T(0);
+            V s = (k == r) ? V(1) : V(0);
 #pragma unroll
             for (int m = r; m < k; ++m) s -= L[k][m] * Gj[r][m];
             Gj[r][k] = s * Ld[k];
@@ -538,84 +629,92 @@ __device__ __forceinline__ void physics_iteration(const ModelDev<T> &M, EnvRegs<
         }
         Aj[r] = rcp_t(a * M.cfm1_joint);
         bj[r] = b;
-        jact[r] = C(SL::FRIC + r) > T(0);
-        if (jact[r]) {   // warm start
-            const T l = C(SL::LAM + r);
+        // warm start; a row without friction (bound 0) starts from 0 and, its bound being 0, stays there
+        const V l = sel_t(gt_t(C(SL::FRIC + r), V(0)), C(SL::LAM + r), V(0));
 #pragma unroll
-            for (int k = r; k < N; ++k) z[k] += Gj[r][k] * l;
-        } else C(SL::LAM + r) = 0;
+        for (int k = r; k < N; ++k) z[k] += Gj[r][k] * l;
+        C(SL::LAM + r) = l;
     }
-    T Gc[NC][3][N];
-    T Ac[NC][3];
-    T bc[NC][3];     // row velocity before impulses, minus the target (penetration correction)
-    bool act[NC];
+    V Gc[NC][3][N];
+    V Ac[NC][3];
+    V bc[NC][3];     // row velocity before impulses, minus the target (penetration correction)
+    bool act[NC];    // some env of this thread presses proxy c into the ground
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
-        const T cz = C(SL::CX + 3 * c + 2);
-        const T depth = M.contact_radius[c] - cz;
-        act[c] = depth > T(0);
+        const V cz = C(SL::CX + 3 * c + 2);
+        const V depth = V(M.contact_radius[c]) - cz;
+        const Mask on_c = gt_t(depth, V(0));
+        act[c] = any_t(on_c);
         if (act[c]) {
-            const T bounce = fmin_t(depth * M.erp_over_dt, M.max_erv);
-            const T x[3] = {C(SL::CX + 3 * c), C(SL::CX + 3 * c + 1), cz - M.contact_radius[c]};   // lowest point
-            T J[3][N];   // rows: normal (z), tangent x, tangent y
+            const V bounce = fmin_t(depth * M.erp_over_dt, V(M.max_erv));
+            const V x[3] = {C(SL::CX + 3 * c), C(SL::CX + 3 * c + 1), cz - M.contact_radius[c]};   // lowest point
+            V J[3][N];   // rows: normal (z), tangent x, tangent y
 #pragma unroll
             for (int i = 0; i < N; ++i) {
-                const T rr[3] = {x[0] - P[i][0], x[1] - P[i][1], x[2] - P[i][2]};
-                T jc[3];
+                const V rr[3] = {x[0] - P[i][0], x[1] - P[i][1], x[2] - P[i][2]};
+                V jc[3];
                 OS2R_CROSS(jc, ax[i], rr);
                 const bool on = i <= M.contact_body[c];
-                J[0][i] = on ? jc[2] : T(0);
-                J[1][i] = on ? jc[0] : T(0);
-                J[2][i] = on ? jc[1] : T(0);
+                J[0][i] = on ? jc[2] : V(0);
+                J[1][i] = on ? jc[0] : V(0);
+                J[2][i] = on ? jc[1] : V(0);
             }
 #pragma unroll
             for (int d = 0; d < 3; ++d) {
-                T a = 0, b = (d == 0) ? -bounce : T(0);
+                V a = V(0), b = (d == 0) ? -bounce : V(0);
 #pragma unroll
                 for (int k = 0; k < N; ++k) {
-                    T s = J[d][k];
+                    V s = J[d][k];
 #pragma unroll
                     for (int m = 0; m < k; ++m) s -= L[k][m] * Gc[c][d][m];
                     Gc[c][d][k] = s * Ld[k];
                     a += Gc[c][d][k] * Gc[c][d][k];
                     b += Gc[c][d][k] * z0[k];
                 }
-                Ac[c][d] = rcp_t(a * M.cfm1_contact);
-                bc[c][d] = b;
-                const T l = C(SL::LAM + N + 3 * c + d);   // warm start
+                // An env of the pair that is NOT in contact gets a dead row: relaxation factor, row velocity and
+                // impulse 0, so every update below computes lam' = 0, dlam = 0 for it (a single-env build never
+                // gets here for such an env: the selects are no-ops).
+                Ac[c][d] = sel_t(on_c, rcp_t(a * M.cfm1_contact), V(0));
+                bc[c][d] = sel_t(on_c, b, V(0));
+                const V l = sel_t(on_c, C(SL::LAM + N + 3 * c + d), V(0));   // warm start
 #pragma unroll
                 for (int k = 0; k < N; ++k) z[k] += Gc[c][d][k] * l;
+                C(SL::LAM + N + 3 * c + d) = l;
             }
         } else {
 #pragma unroll
-            for (int d = 0; d < 3; ++d) C(SL::LAM + N + 3 * c + d) = 0;
+            for (int d = 0; d < 3; ++d) C(SL::LAM + N + 3 * c + d) = V(0);
         }
     }
     // ---- projected Gauss-Seidel sweeps in whitened coordinates -------------------------------------------
     // Row update with relative CFM c on the diagonal A(1+c):
     //   lam' = clamp(lam - (G.z - target + c*A*lam) / (A(1+c))) = clamp(lam*(1-k) - (G.z - target)*inv),
     //   1-k = 1/(1+c), inv = 1/(A(1+c)) precomputed per row.
-    // Early exit (per env): the sweeps of a lane end after the first sweep whose whitened velocity change
+    // Early exit (per env): the sweeps of an env end after the first sweep whose whitened velocity change
     // |dz| = sqrt(dv^T M dv) is <= pgs_tol (tol 0: only when the sweep left z bit-for-bit unchanged, the typical
-    // case being saturated joint friction without contact). The decision uses the lane's own data only, so a
-    // result never depends on which other envs share the warp; the warp leaves the loop when its last lane does.
+    // case being saturated joint friction without contact). The decision uses the env's own data only, so a
+    // result never depends on which other envs share the thread or the warp: in the pair build an env that has
+    // finished is FROZEN (its rows keep their impulses, dlam = 0) while its partner sweeps on; the warp leaves the
+    // loop when its last env does.
     const T kj1 = M.kj1, kc1 = M.kc1;   // 1 - k
-    const T tol2 = M.pgs_tol2;
+    const V tol2 = V(M.pgs_tol2);
+    Mask live = all_true<V>();
 #pragma unroll 1
     for (int it = 0; it < M.pgs_iters; ++it) {
-        T zs[N];
+        V zs[N];
 #pragma unroll
         for (int k = 0; k < N; ++k) zs[k] = z[k];
 #pragma unroll
         for (int r = 0; r < N; ++r) {
             // branch-free: a row without friction has bound 0, so its impulse stays 0 and the update adds 0
-            const T lam = C(SL::LAM + r), lim = C(SL::FRIC + r);
-            T w = bj[r];
+            const V lam = C(SL::LAM + r), lim = C(SL::FRIC + r);
+            V w = bj[r];
 #pragma unroll
             for (int k = r; k < N; ++k) w += Gj[r][k] * z[k];
-            T nl = lam * kj1 - w * Aj[r];
+            V nl = lam * kj1 - w * Aj[r];
             nl = fmax_t(-lim, fmin_t(lim, nl));
-            const T dl = nl - lam;
+            if constexpr (VT<V>::LANES > 1) nl = sel_t(live, nl, lam);
+            const V dl = nl - lam;
 #pragma unroll
             for (int k = r; k < N; ++k) z[k] += Gj[r][k] * dl;
             C(SL::LAM + r) = nl;
@@ -623,64 +722,67 @@ __device__ __forceinline__ void physics_iteration(const ModelDev<T> &M, EnvRegs<
 #pragma unroll
         for (int c = 0; c < NC; ++c) {
             if (act[c]) {
-                T ln = C(SL::LAM + N + 3 * c);
+                V ln = C(SL::LAM + N + 3 * c);
 #pragma unroll
                 for (int d = 0; d < 3; ++d) {
                     const int r = N + 3 * c + d;
-                    const T lam = (d == 0) ? ln : C(SL::LAM + r);
-                    T w = bc[c][d];
+                    const V lam = (d == 0) ? ln : C(SL::LAM + r);
+                    V w = bc[c][d];
 #pragma unroll
                     for (int k = 0; k < N; ++k) w += Gc[c][d][k] * z[k];
-                    T nl = lam * kc1 - w * Ac[c][d];
-                    if (d == 0) { nl = fmax_t(nl, T(0)); ln = nl; }
+                    V nl = lam * kc1 - w * Ac[c][d];
+                    if (d == 0) nl = fmax_t(nl, V(0));
                     else {
-                        const T lim = C(SL::MU + c) * ln;
+                        const V lim = C(SL::MU + c) * ln;
                         nl = fmax_t(-lim, fmin_t(lim, nl));
                     }
-                    const T dl = nl - lam;
+                    if constexpr (VT<V>::LANES > 1) nl = sel_t(live, nl, lam);
+                    if (d == 0) ln = nl;
+                    const V dl = nl - lam;
 #pragma unroll
                     for (int k = 0; k < N; ++k) z[k] += Gc[c][d][k] * dl;
                     C(SL::LAM + r) = nl;
                 }
             }
         }
-        T e2 = 0;
+        V e2 = V(0);
 #pragma unroll
-        for (int k = 0; k < N; ++k) { const T dz = z[k] - zs[k]; e2 += dz * dz; }
-        if (e2 <= tol2) break;
+        for (int k = 0; k < N; ++k) { const V dz = z[k] - zs[k]; e2 += dz * dz; }
+        live = and_not(live, le_t(e2, tol2));
+        if (!any_t(live)) break;
     }
     // ---- v = v* + L^-T z ; q += dt v  (TwoSum-compensated (hi, lo) pairs in fp32) --------------------------
     {
-        T dv[N];
+        V dv[N];
 #pragma unroll
         for (int i = N - 1; i >= 0; --i) {
-            T s = z[i];
+            V s = z[i];
 #pragma unroll
             for (int k = i + 1; k < N; ++k) s -= L[k][i] * dv[k];
             dv[i] = s * Ld[i];
         }
 #pragma unroll
         for (int i = 0; i < N; ++i) {
-            if (sizeof(T) == 4) {
+            if constexpr (FP32) {
                 {   // velocity: measured 10x less drift over 1000 steps than plain fp32 accumulation
-                    const T b = (dvq[i] + dv[i]) + C(SL::VLO + i);
-                    const T a = E.v[i];
-                    const T s = a + b;
-                    const T bb = s - a;
+                    const V b = (dvq[i] + dv[i]) + C(SL::VLO + i);
+                    const V a = E.v[i];
+                    const V s = a + b;
+                    const V bb = s - a;
                     C(SL::VLO + i) = (a - (s - bb)) + (b - bb);
                     E.v[i] = s;
                 }
                 {   // position
-                    const T b = dt * E.v[i] + C(SL::QLO + i);
-                    const T a = E.q_hi[i];
-                    const T s = a + b;
-                    const T bb = s - a;
+                    const V b = E.v[i] * dt + C(SL::QLO + i);
+                    const V a = E.q_hi[i];
+                    const V s = a + b;
+                    const V bb = s - a;
                     C(SL::QLO + i) = (a - (s - bb)) + (b - bb);
                     E.q_hi[i] = s;
                 }
             } else {
                 E.v[i] = vs[i] + dv[i];
-                E.q_hi[i] += dt * E.v[i];
+                E.q_hi[i] += E.v[i] * dt;
             }
         }
     }

@@ -82,28 +82,36 @@ __global__ void __launch_bounds__(OS2R_BLOCK) init_kernel(const __grid_constant_
 }
 
 // ------------------------------------------------------------------------------------------------
-// lane sorting: which env of the block's window each thread steps
+// lane sorting: which env(s) of the block's window each thread steps
 // ------------------------------------------------------------------------------------------------
 // A warp pays for the union of its lanes' constraint rows (each contact proxy costs ~780 instructions per
 // physics iteration as soon as ONE lane touches the ground), so the block regroups its envs by the set of
-// proxies that were near the ground after the previous step: envs lying on the ground share a warp, hopping
-// envs share the next ones, airborne envs fill the rest and never execute contact rows. Stable counting sort
-// over 2^NC classes (+1 for slots past the end of the batch), ballot/match based, once per env step.
-// The hint only decides the thread <-> env pairing; every per-env result is independent of it.
-template <int BLOCK, int NKEYS>
-__device__ __forceinline__ int sorted_source(int key, int *scratch) {
+// proxies that were near the ground after the previous step: envs lying on the ground share a warp (and, in the pair
+// build, a thread), hopping envs share the next ones, airborne envs fill the rest and never execute contact rows.
+// Stable counting sort of the window's BLOCK * LANES envs over 2^NC classes (+1 for slots past the end of the batch),
+// ballot/match based, once per env step: window slot h * BLOCK + tid carries key[h]; thread t then steps the envs at
+// sorted positions LANES * t .. LANES * t + LANES - 1. The hint only decides the thread <-> env pairing; every per-env
+// result is independent of it.
+template <int BLOCK, int LANES, int NKEYS>
+__device__ __forceinline__ void sorted_sources(const int (&key)[LANES], int (&src)[LANES], int *scratch) {
     constexpr int W = BLOCK / 32;
-    constexpr int CNT = NKEYS * W;                 // counters, ordered (heavier class first, then warp)
+    constexpr int WL = W * LANES;
+    constexpr int CNT = NKEYS * WL;                // counters, ordered (heavier class first, then half, then warp)
     constexpr int PER = (CNT + 31) / 32;           // counters scanned by each lane of warp 0
     constexpr int CPAD = PER * 32;
     int *cnt = scratch;              // [CPAD] counts, then exclusive offsets
-    int *perm = scratch + CPAD;      // [BLOCK]
+    int *perm = scratch + CPAD;      // [BLOCK * LANES]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int k = tid; k < CPAD; k += BLOCK) cnt[k] = 0;
     __syncthreads();
-    const unsigned same = __match_any_sync(0xffffffffu, key);
-    const int p = (NKEYS - 1 - key) * W + warp;
-    if (lane == __ffs(same) - 1) cnt[p] = __popc(same);
+    unsigned same[LANES];
+    int p[LANES];
+#pragma unroll
+    for (int h = 0; h < LANES; ++h) {
+        same[h] = __match_any_sync(0xffffffffu, key[h]);
+        p[h] = (NKEYS - 1 - key[h]) * WL + h * W + warp;
+        if (lane == __ffs(same[h]) - 1) cnt[p[h]] = __popc(same[h]);
+    }
     __syncthreads();
     if (warp == 0) {
         int v[PER], s = 0;
@@ -120,97 +128,131 @@ __device__ __forceinline__ int sorted_source(int key, int *scratch) {
         for (int k = 0; k < PER; ++k) { cnt[PER * lane + k] = run; run += v[k]; }
     }
     __syncthreads();
-    perm[cnt[p] + __popc(same & ((1u << lane) - 1u))] = tid;
+#pragma unroll
+    for (int h = 0; h < LANES; ++h) perm[cnt[p[h]] + __popc(same[h] & ((1u << lane) - 1u))] = h * BLOCK + tid;
     __syncthreads();
-    const int src = perm[tid];
+#pragma unroll
+    for (int h = 0; h < LANES; ++h) src[h] = perm[LANES * tid + h];
     __syncthreads();                 // the scratch area is reused for the cold slots
-    return src;
+}
+
+// gather one value per env of the thread into a V
+template <typename V>
+__device__ __forceinline__ V gather(const typename VT<V>::S *p, const int64_t (&e)[VT<V>::LANES]) {
+    if constexpr (VT<V>::LANES == 2) return V(__ldcg(p + e[0]), __ldcg(p + e[1]));
+    else return __ldcg(p + e[0]);
+}
+template <typename V>
+__device__ __forceinline__ V from_halves(const float (&x)[VT<V>::LANES]) {
+    if constexpr (VT<V>::LANES == 2) return V(x[0], x[1]);
+    else return (V)x[0];
 }
 
 // ------------------------------------------------------------------------------------------------
 // the fused step kernel: substeps x physics + observation + reward + done + auto-reset
 // ------------------------------------------------------------------------------------------------
-// LONE = the build for batches of at most four 2-warp blocks per SM (every batch below the wide-block threshold): no
-// occupancy target, so ptxas takes ~200-225 registers instead of 128 and schedules for instruction-level parallelism
-// (with one or two warps per scheduler a warp is bound by its own dependency chains): 4-12 % lower step latency.
-template <typename T, int N, int NC, int BLOCK, bool DAMPED, bool LONE>
-__global__ void __launch_bounds__(BLOCK, (sizeof(T) == 4 && !LONE ? OS2R_RESIDENT_THREADS / BLOCK : 1))
-step_kernel(const __grid_constant__ ModelDev<T> M, const __grid_constant__ TaskDev K, StateDev<T> S,
-            const __grid_constant__ StepIO IO, StatsDev *stats) {
+// V = float : the product build, one env per thread. Batches of >= one 224-thread block per SM run 7-warp blocks, two
+//     per SM (MINB = 2: 128 registers per thread; 65 536 envs = 293 blocks = ONE wave of 14 warps per SM); smaller
+//     batches run 2-warp blocks without an occupancy target (MINB = 1: ptxas takes ~200-225 registers and schedules for
+//     instruction-level parallelism — with one or two warps per scheduler a warp is bound by its own dependency chains);
+// V = double: the fp64 verification build, one env per thread;
+// V = f2    : TWO envs per thread through the packed fp32x2 instructions of sm_100 (FFMA2 / FMUL2 / FADD2), one block
+//     per SM at up to 255 registers per thread. Measured slower than the float build on this latency-bound kernel
+//      and therefore opt-in (os2r_tuning.force_pair); results agree with the float build to
+//     rounding but are not bit-identical (ptxas contracts packed mul + add pairs on its own).
+template <typename V, int N, int NC, int BLOCK, bool DAMPED, int MINB>
+__global__ void __launch_bounds__(BLOCK, MINB)
+step_kernel(const __grid_constant__ ModelDev<typename VT<V>::S> M, const __grid_constant__ TaskDev K,
+            StateDev<typename VT<V>::S> S, const __grid_constant__ StepIO IO, StatsDev *stats) {
+    using T = typename VT<V>::S;
+    constexpr int LANES = VT<V>::LANES;
+    constexpr int EPB = BLOCK * LANES;             // envs per block
     const float *__restrict__ actions = IO.actions;
     float *__restrict__ obs = IO.obs;
     float *__restrict__ reward = IO.reward;
     uint8_t *__restrict__ done = IO.done;
     float *__restrict__ term_obs = IO.term_obs;
     int32_t *__restrict__ info = IO.info;
-    static_assert(NC <= 3, "class byte: one bit per contact proxy, 2^NC + 1 sort keys");
+    static_assert(NC <= 6, "class byte: one bit per contact proxy, 2^NC + 1 sort keys");
     const int64_t NE = S.n_envs;
     using SL = ColdSlots<N, NC>;
     constexpr int ROWS = SL::ROWS;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    // Thread t steps env (block window start + src). Slots past the end of the batch (last block only) sort last
-    // and shadow the last env instead of exiting, so that the block-wide barriers inside the physics loop stay
-    // legal; they leave before anything is written.
-    const int64_t window = (int64_t)blockIdx.x * BLOCK;
-    const bool nominal_valid = window + threadIdx.x < NE;
-    const int key = nominal_valid ? 1 + (int)(__ldcg(S.cls + window + threadIdx.x) & ((1u << NC) - 1u)) : 0;
-    // While the class byte travels and the block sorts, pull the window's state lines towards the L2: which env a
-    // thread will step is not known yet, but it is one of this window's, so the DRAM latency of the prologue loads
-    // overlaps the sort instead of following it.
-    if (nominal_valid) {
-        const int64_t en = window + threadIdx.x;
-        auto pf = [](const void *ptr) { asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr)); };
+    // Thread t steps the envs at sorted positions LANES*t.. of the block's window. Slots past the end of the batch (last
+    // block only) sort last and shadow the last env instead of exiting, so that the block-wide barriers inside the
+    // physics loop stay legal; they are skipped by the epilogue, before anything is written.
+    const int64_t window = (int64_t)blockIdx.x * EPB;
+    int key[LANES];
 #pragma unroll
-        for (int i = 0; i < N; ++i) {
-            pf(S.q_hi + i * NE + en); pf(S.qd + i * NE + en); pf(S.q_lo + i * NE + en); pf(S.qd_lo + i * NE + en);
-            pf(S.mass_scale + i * NE + en); pf(S.damping + i * NE + en); pf(S.friction + i * NE + en);
+    for (int h = 0; h < LANES; ++h) {
+        const int64_t en = window + h * BLOCK + threadIdx.x;
+        const bool nominal_valid = en < NE;
+        key[h] = nominal_valid ? 1 + (int)(__ldcg(S.cls + en) & ((1u << NC) - 1u)) : 0;
+        // While the class byte travels and the block sorts, pull the window's state lines towards the L2: which env a
+        // thread will step is not known yet, but it is one of this window's, so the DRAM latency of the prologue loads
+        // overlaps the sort instead of following it.
+        if (nominal_valid) {
+            auto pf = [](const void *ptr) { asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr)); };
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                pf(S.q_hi + i * NE + en); pf(S.qd + i * NE + en); pf(S.q_lo + i * NE + en); pf(S.qd_lo + i * NE + en);
+                pf(S.mass_scale + i * NE + en); pf(S.damping + i * NE + en); pf(S.friction + i * NE + en);
+            }
+#pragma unroll
+            for (int r = 0; r < ROWS; ++r) pf(S.lam + r * NE + en);
+#pragma unroll
+            for (int c = 0; c < NC; ++c) pf(S.mu + c * NE + en);
+            pf(S.gravity_z + en); pf(S.a_prev + en); pf(S.a_prev + NE + en); pf(S.steps + en); pf(S.reset_id + en);
+            pf(S.ret + en); pf(reinterpret_cast<const float2 *>(IO.actions) + en);
         }
-#pragma unroll
-        for (int r = 0; r < ROWS; ++r) pf(S.lam + r * NE + en);
-#pragma unroll
-        for (int c = 0; c < NC; ++c) pf(S.mu + c * NE + en);
-        pf(S.gravity_z + en); pf(S.a_prev + en); pf(S.a_prev + NE + en); pf(S.steps + en); pf(S.reset_id + en);
-        pf(S.ret + en); pf(reinterpret_cast<const float2 *>(IO.actions) + en);
     }
-    const int src = sorted_source<BLOCK, (1 << NC) + 1>(key, reinterpret_cast<int *>(smem_raw));
-    const int64_t e_raw = window + src;
-    const bool valid = e_raw < NE;
-    const int64_t e = valid ? e_raw : NE - 1;
-    const Cold<T, BLOCK> C{reinterpret_cast<T *>(smem_raw) + threadIdx.x};
+    int src[LANES];
+    sorted_sources<BLOCK, LANES, (1 << NC) + 1>(key, src, reinterpret_cast<int *>(smem_raw));
+    int64_t e[LANES];
+    bool valid[LANES];
+#pragma unroll
+    for (int h = 0; h < LANES; ++h) {
+        const int64_t e_raw = window + src[h];
+        valid[h] = e_raw < NE;
+        e[h] = valid[h] ? e_raw : NE - 1;
+    }
+    const Cold<V, BLOCK> C{reinterpret_cast<V *>(smem_raw) + threadIdx.x};
 
-    EnvRegs<T, N> E;
+    EnvRegs<V, N> E;
     // ---- prologue: ALL global loads are issued back to back (explicit ld.global, so the compiler may hoist
     //      them above the shared-memory stores that follow; generic loads were serialised LD -> STS -> LD ...,
     //      one DRAM round trip each) and only then scattered into registers / shared memory.
-    T ld_qlo[N], ld_vlo[N], ld_mass[N], ld_damp[N], ld_fric[N], ld_lam[ROWS], ld_mu[NC];
+    V ld_qlo[N], ld_vlo[N], ld_mass[N], ld_damp[N], ld_fric[N], ld_lam[ROWS], ld_mu[NC];
 #pragma unroll
     for (int i = 0; i < N; ++i) {
-        E.q_hi[i] = __ldcg(S.q_hi + i * NE + e);
-        E.v[i] = __ldcg(S.qd + i * NE + e);
-        ld_qlo[i] = __ldcg(S.q_lo + i * NE + e);
-        ld_vlo[i] = __ldcg(S.qd_lo + i * NE + e);
-        ld_mass[i] = __ldcg(S.mass_scale + i * NE + e);
-        ld_damp[i] = __ldcg(S.damping + i * NE + e);
-        ld_fric[i] = __ldcg(S.friction + i * NE + e);
+        E.q_hi[i] = gather<V>(S.q_hi + i * NE, e);
+        E.v[i] = gather<V>(S.qd + i * NE, e);
+        ld_qlo[i] = gather<V>(S.q_lo + i * NE, e);
+        ld_vlo[i] = gather<V>(S.qd_lo + i * NE, e);
+        ld_mass[i] = gather<V>(S.mass_scale + i * NE, e);
+        ld_damp[i] = gather<V>(S.damping + i * NE, e);
+        ld_fric[i] = gather<V>(S.friction + i * NE, e);
     }
 #pragma unroll
-    for (int r = 0; r < ROWS; ++r) ld_lam[r] = __ldcg(S.lam + r * NE + e);
+    for (int r = 0; r < ROWS; ++r) ld_lam[r] = gather<V>(S.lam + r * NE, e);
 #pragma unroll
-    for (int c = 0; c < NC; ++c) ld_mu[c] = __ldcg(S.mu + c * NE + e);
-    E.gz = __ldcg(S.gravity_z + e);
-    const T a_old0 = __ldcg(S.a_prev + e), a_old1 = __ldcg(S.a_prev + NE + e);
-    const int steps_in = __ldcg(S.steps + e);
-    int reset_idx = __ldcg(S.reset_id + e);
-    const double ret_in = __ldcg(S.ret + e);
-    float2 act = __ldcg(reinterpret_cast<const float2 *>(actions) + e);
-    // A non-finite action (the reference rejects it through `assert action_space.contains`, tasks/monopod.py:218)
-    // applies no torque and takes the non-finite path of the epilogue: defined outputs, forced reset, counted.
-    // fminf / fmaxf would silently turn a NaN into a full negative torque.
-    const bool act_finite = isfinite(act.x) && isfinite(act.y);
-    if (!act_finite) { act.x = 0.0f; act.y = 0.0f; }
-    // ScenarIO clips force targets to +-max force (tasks/monopod.py:313-316)
-    act.x = fminf(1.0f, fmaxf(-1.0f, act.x));
-    act.y = fminf(1.0f, fmaxf(-1.0f, act.y));
+    for (int c = 0; c < NC; ++c) ld_mu[c] = gather<V>(S.mu + c * NE, e);
+    E.gz = gather<V>(S.gravity_z, e);
+    float ax_[LANES], ay_[LANES], afin_[LANES];
+#pragma unroll
+    for (int h = 0; h < LANES; ++h) {
+        float2 act = __ldcg(reinterpret_cast<const float2 *>(actions) + e[h]);
+        // A non-finite action (the reference rejects it through `assert action_space.contains`, tasks/monopod.py:218)
+        // applies no torque and takes the non-finite path of the epilogue: defined outputs, forced reset, counted.
+        // fminf / fmaxf alone would silently turn a NaN into a full negative torque.
+        const bool fin = isfinite(act.x) && isfinite(act.y);
+        if (!fin) { act.x = 0.0f; act.y = 0.0f; }
+        // ScenarIO clips force targets to +-max force (tasks/monopod.py:313-316)
+        ax_[h] = fminf(1.0f, fmaxf(-1.0f, act.x));
+        ay_[h] = fminf(1.0f, fmaxf(-1.0f, act.y));
+        afin_[h] = fin ? 1.0f : 0.0f;
+    }
+    const V act_x = from_halves<V>(ax_), act_y = from_halves<V>(ay_);
 #pragma unroll
     for (int i = 0; i < N; ++i) {
         C(SL::QLO + i) = ld_qlo[i];
@@ -218,9 +260,9 @@ step_kernel(const __grid_constant__ ModelDev<T> M, const __grid_constant__ TaskD
         C(SL::MASS + i) = ld_mass[i];
         C(SL::DAMP + i) = ld_damp[i];
         C(SL::FRIC + i) = ld_fric[i] * M.dt;
-        T tau = T(0);
-        if (i == M.hip_dof) tau = M.max_torque[0] * (T)act.x;
-        if (i == M.knee_dof) tau = M.max_torque[1] * (T)act.y;
+        V tau = V(0);
+        if (i == M.hip_dof) tau = act_x * M.max_torque[0];
+        if (i == M.knee_dof) tau = act_y * M.max_torque[1];
         C(SL::TAU + i) = tau;
     }
 #pragma unroll
@@ -228,100 +270,107 @@ step_kernel(const __grid_constant__ ModelDev<T> M, const __grid_constant__ TaskD
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
         C(SL::MU + c) = ld_mu[c];
-        C(SL::CX + 3 * c + 2) = T(0);   // defined even when substeps == 0 (reads as "near")
+        C(SL::CX + 3 * c + 2) = V(0);   // defined even when substeps == 0 (reads as "near")
     }
-    C(SL::AOLD) = a_old0;
-    C(SL::AOLD + 1) = a_old1;
-    C(SL::MISC) = __int_as_float_t<T>(steps_in);
-    C(SL::MISC + 1) = __int_as_float_t<T>(__double2loint(ret_in));
-    C(SL::MISC + 2) = __int_as_float_t<T>(__double2hiint(ret_in));
+    C(SL::ACT) = act_x;
+    C(SL::ACT + 1) = act_y;
+    C(SL::AFIN) = from_halves<V>(afin_);
 
 #pragma unroll 1
     for (int s = 0; s < M.substeps; ++s) {
-        // Keep the block's warps in phase: all warps of an SM run the same ~41 KB loop body, and warps that drift
-        // apart thrash the instruction caches (measured: -3..4 % step time with the two barriers per iteration;
-        // a rolled forward pass that fits the 32 KB cache still lost 12 % without them and 20 % overall to its
-        // extra instructions and spills — DESIGN.md section 9).
+        // Keep the block's warps in phase: all warps of an SM run the same ~40 KB loop body, and warps that drift
+        // apart thrash the instruction caches.
         __syncthreads();
-        physics_iteration<T, N, NC, DAMPED, Cold<T, BLOCK>>(M, E, C);
+        physics_iteration<V, N, NC, DAMPED, Cold<V, BLOCK>>(M, E, C);
     }
-    if (!valid) return;
-
-    // ---- epilogue (fp64, once per env step) --------------------------------------------------------
-    double q[N], v[N];
-    bool finite = act_finite;
+    // ---- epilogue (fp64, once per ENV): the hot registers are parked next to the cold slots and every env of the
+    //      thread is finished from shared memory, one after the other, by the same (rolled) code
 #pragma unroll
-    for (int i = 0; i < N; ++i) {
-        q[i] = (double)E.q_hi[i] + (double)C(SL::QLO + i);
-        v[i] = (double)E.v[i] + (double)C(SL::VLO + i);
-        finite = finite && isfinite(q[i]) && isfinite(v[i]);
-    }
-    if (!finite) {   // nothing non-finite leaves the kernel: the step reports a zero observation and reward
-#pragma unroll
-        for (int i = 0; i < N; ++i) { q[i] = 0.0; v[i] = 0.0; }
-    }
-    const double a0[2] = {(double)act.x, (double)act.y};
-    const double a_old[2] = {(double)C(SL::AOLD), (double)C(SL::AOLD + 1)};
-    double o[OS2R_MAX_OBS];
-    const bool task_done = observe<N>(K, q, v, a_old, o);
-    const double r = finite ? reward_fn(K.cfg, o, a0, a_old) : 0.0;
-    const int D = K.cfg.obs_dim;
-    int cause = (task_done && finite) ? 1 : 0;
-    if (!finite) cause = 4;
-    const int steps = __float_as_int_t<T>(C(SL::MISC)) + 1;
-    const double ret = __hiloint2double(__float_as_int_t<T>(C(SL::MISC + 2)), __float_as_int_t<T>(C(SL::MISC + 1))) + r;
-    if (K.cfg.max_episode_steps > 0 && steps >= K.cfg.max_episode_steps) cause |= 2;
-
-    reward[e] = (float)r;
-    done[e] = cause != 0;
-    if (term_obs) for (int k = 0; k < D; ++k) term_obs[e * D + k] = (float)o[k];
-    S.a_prev[e] = (T)act.x;
-    S.a_prev[NE + e] = (T)act.y;
-
-    if (cause && IO.term_count) {
-        const int k = atomicAdd(IO.term_count, 1);
-        if (k < IO.term_cap) {
-            int32_t *rec = IO.term_records + (int64_t)k * (D + 2);
-            rec[0] = (int32_t)e;
-            rec[1] = cause;
-            for (int c = 0; c < D; ++c) rec[2 + c] = __float_as_int((float)o[c]);
-        }
-    }
-    if (cause) {
-        atomicAdd(&stats->episodes, 1ull);
-        if (cause & 1) atomicAdd(&stats->done_task, 1ull);
-        if (cause & 2) atomicAdd(&stats->done_timelimit, 1ull);
-        if (cause & 4) atomicAdd(&stats->nonfinite_resets, 1ull);
-        atomicAdd(&stats->sum_return, ret);
-        atomicAdd(&stats->sum_length, (double)steps);
-    }
-    if (cause && (K.cfg.auto_reset || !finite)) {
-        reset_idx = reset_env_global<T, N, NC>(K, S, e, a_old, obs + e * D);   // also marks the env "unknown" (all near)
-    } else {
-        // next step's sorting hint: which proxies ended within sort_margin of the ground
-        unsigned cls = 0;
-#pragma unroll
-        for (int c = 0; c < NC; ++c)
-            if (!(C(SL::CX + 3 * c + 2) - M.contact_radius[c] >= M.sort_margin)) cls |= 1u << c;
-        S.cls[e] = (uint8_t)cls;
+    for (int i = 0; i < N; ++i) { C(SL::QHI + i) = E.q_hi[i]; C(SL::VHI + i) = E.v[i]; }
+#pragma unroll 1
+    for (int h = 0; h < LANES; ++h) {
+        const bool ok = LANES == 1 ? valid[0] : (h ? valid[LANES - 1] : valid[0]);
+        if (!ok) continue;
+        const int64_t en = LANES == 1 ? e[0] : (h ? e[LANES - 1] : e[0]);
+        const int steps_in = __ldcg(S.steps + en);
+        int reset_idx = __ldcg(S.reset_id + en);
+        const double ret_in = __ldcg(S.ret + en);
+        const double a_old[2] = {(double)__ldcg(S.a_prev + en), (double)__ldcg(S.a_prev + NE + en)};
+        const float actx = (float)C.half(SL::ACT, h), acty = (float)C.half(SL::ACT + 1, h);
+        double q[N], v[N];
+        bool finite = C.half(SL::AFIN, h) != T(0);
 #pragma unroll
         for (int i = 0; i < N; ++i) {
-            S.q_hi[i * NE + e] = E.q_hi[i];
-            S.q_lo[i * NE + e] = C(SL::QLO + i);
-            S.qd[i * NE + e] = E.v[i];
-            S.qd_lo[i * NE + e] = C(SL::VLO + i);
+            q[i] = (double)C.half(SL::QHI + i, h) + (double)C.half(SL::QLO + i, h);
+            v[i] = (double)C.half(SL::VHI + i, h) + (double)C.half(SL::VLO + i, h);
+            finite = finite && isfinite(q[i]) && isfinite(v[i]);
         }
+        if (!finite) {   // nothing non-finite leaves the kernel: the step reports a zero state's observation, reward 0
 #pragma unroll
-        for (int rr = 0; rr < ROWS; ++rr) S.lam[rr * NE + e] = C(SL::LAM + rr);
-        S.steps[e] = steps;
-        S.ret[e] = ret;
-        for (int k = 0; k < D; ++k) obs[e * D + k] = (float)o[k];
+            for (int i = 0; i < N; ++i) { q[i] = 0.0; v[i] = 0.0; }
+        }
+        const double a0[2] = {(double)actx, (double)acty};
+        double o[OS2R_MAX_OBS];
+        const bool task_done = observe<N>(K, q, v, a_old, o);
+        const double r = finite ? reward_fn(K.cfg, o, a0, a_old) : 0.0;
+        const int D = K.cfg.obs_dim;
+        int cause = (task_done && finite) ? 1 : 0;
+        if (!finite) cause = 4;
+        const int steps = steps_in + 1;
+        const double ret = ret_in + r;
+        if (K.cfg.max_episode_steps > 0 && steps >= K.cfg.max_episode_steps) cause |= 2;
+
+        reward[en] = (float)r;
+        done[en] = cause != 0;
+        if (term_obs) for (int k = 0; k < D; ++k) term_obs[en * D + k] = (float)o[k];
+        S.a_prev[en] = (T)actx;
+        S.a_prev[NE + en] = (T)acty;
+
+        if (cause && IO.term_count) {
+            const int k = atomicAdd(IO.term_count, 1);
+            if (k < IO.term_cap) {
+                int32_t *rec = IO.term_records + (int64_t)k * (D + 2);
+                rec[0] = (int32_t)en;
+                rec[1] = cause;
+                for (int c = 0; c < D; ++c) rec[2 + c] = __float_as_int((float)o[c]);
+            }
+        }
+        if (cause) {
+            atomicAdd(&stats->episodes, 1ull);
+            if (cause & 1) atomicAdd(&stats->done_task, 1ull);
+            if (cause & 2) atomicAdd(&stats->done_timelimit, 1ull);
+            if (cause & 4) atomicAdd(&stats->nonfinite_resets, 1ull);
+            atomicAdd(&stats->sum_return, ret);
+            atomicAdd(&stats->sum_length, (double)steps);
+        }
+        if (cause && (K.cfg.auto_reset || !finite)) {
+            reset_idx = reset_env_global<T, N, NC>(K, S, en, a_old, obs + en * D);   // also marks the env "unknown" (all near)
+        } else {
+            // next step's sorting hint: which proxies ended within sort_margin of the ground
+            unsigned cls = 0;
+#pragma unroll
+            for (int c = 0; c < NC; ++c)
+                if (!(C.half(SL::CX + 3 * c + 2, h) - M.contact_radius[c] >= M.sort_margin)) cls |= 1u << c;
+            S.cls[en] = (uint8_t)cls;
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                S.q_hi[i * NE + en] = C.half(SL::QHI + i, h);
+                S.q_lo[i * NE + en] = C.half(SL::QLO + i, h);
+                S.qd[i * NE + en] = C.half(SL::VHI + i, h);
+                S.qd_lo[i * NE + en] = C.half(SL::VLO + i, h);
+            }
+#pragma unroll
+            for (int rr = 0; rr < ROWS; ++rr) S.lam[rr * NE + en] = C.half(SL::LAM + rr, h);
+            S.steps[en] = steps;
+            S.ret[en] = ret;
+            for (int k = 0; k < D; ++k) obs[en * D + k] = (float)o[k];
+        }
+        if (info) {
+            info[2 * en] = reset_idx;
+            info[2 * en + 1] = cause;
+        }
+        if (IO.reset_id8) IO.reset_id8[en] = (uint8_t)reset_idx;
     }
-    if (info) {
-        info[2 * e] = reset_idx;
-        info[2 * e + 1] = cause;
-    }
-    if (IO.reset_id8) IO.reset_id8[e] = (uint8_t)reset_idx;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -342,9 +391,9 @@ __global__ void __launch_bounds__(256) fma_peak_kernel(float *out, int iters, fl
 }
 
 // ------------------------------------------------------------------------------------------------
-// launchers (dispatch on n_dof; all shipped models carry 3 contact proxies)
+// launchers (dispatch on precision / build, n_dof, block width, damping)
 // ------------------------------------------------------------------------------------------------
-static inline int grid_for(int64_t n, int block) { return (int)((n + block - 1) / block); }
+static inline int grid_for(int64_t n, int per_block) { return (int)((n + per_block - 1) / per_block); }
 
 #define OS2R_DISPATCH_N(n_dof, CALL)                 \
     switch (n_dof) {                                 \
@@ -355,56 +404,81 @@ static inline int grid_for(int64_t n, int block) { return (int)((n + block - 1) 
     default: return cudaErrorInvalidValue;           \
     }
 
-template <typename T, int N, int BLOCK>
+template <typename V, int N, int BLOCK>
 static constexpr size_t step_smem_bytes() {
-    size_t cold = (size_t)ColdSlots<N, OS2R_NC>::COUNT * BLOCK * sizeof(T), sort = (size_t)(512 + BLOCK) * sizeof(int);
+    constexpr int LANES = VT<V>::LANES;
+    constexpr int NKEYS = (1 << OS2R_NC) + 1;
+    size_t cold = (size_t)ColdSlots<N, OS2R_NC>::COUNT * BLOCK * sizeof(V);
+    size_t sort = (size_t)(((NKEYS * (BLOCK / 32) * LANES + 31) / 32) * 32 + BLOCK * LANES) * sizeof(int);
     return cold > sort ? cold : sort;
 }
 
-// Wide blocks (7 warps) give the lane sort enough envs to fill whole warps with one class; they need at least one
-// block per SM to pay off. Small batches and the fp64 verification build keep 2-warp blocks (more SMs busy).
-template <typename T>
-int step_block_threads(int64_t n_envs, int sm_count) {
-    if (sizeof(T) == 4 && n_envs >= (int64_t)sm_count * OS2R_BLOCK_WIDE) return OS2R_BLOCK_WIDE;
+// Threads per block of the step kernel for a batch. Wide blocks (7 warps) give the lane sort enough envs to fill whole
+// warps with one contact class; they need about one block per SM to pay off (float: 224 envs per block, pair build: 448).
+// Small batches and the fp64 verification build keep 2-warp blocks (more SMs busy).
+int step_block_threads(int build, int64_t n_envs, int sm_count) {
+    if (build == OS2R_BUILD_F32 && n_envs >= (int64_t)sm_count * OS2R_BLOCK_WIDE) return OS2R_BLOCK_WIDE;
+    if (build == OS2R_BUILD_PAIR && n_envs * 8 >= (int64_t)sm_count * OS2R_BLOCK_WIDE * 2 * 7) return OS2R_BLOCK_WIDE;
     return OS2R_BLOCK;
 }
 
-template <typename T, int N, int BLOCK, bool DAMPED>
-static cudaError_t launch_step_nd(const ModelDev<T> &M, const TaskDev &K, const StateDev<T> &S, const StepIO &io, StatsDev *stats,
-                                  cudaStream_t stream, bool lone) {
-    constexpr size_t smem = step_smem_bytes<T, N, BLOCK>();
-    if constexpr (sizeof(T) == 4 && BLOCK == OS2R_BLOCK) {
-        if (lone) {
-            step_kernel<T, N, OS2R_NC, BLOCK, DAMPED, true><<<grid_for(S.n_envs, BLOCK), BLOCK, smem, stream>>>(M, K, S, io, stats);
-            return cudaGetLastError();
-        }
-    }
-    // blocks that need more than 48 KB of dynamic shared memory were opted in by prepare_step (once per handle,
-    // on the handle's device: the attribute is per device, a process can hold handles on several GPUs)
-    step_kernel<T, N, OS2R_NC, BLOCK, DAMPED, false><<<grid_for(S.n_envs, BLOCK), BLOCK, smem, stream>>>(M, K, S, io, stats);
-    return cudaGetLastError();
-}
-template <typename T, int N, int BLOCK>
-static cudaError_t launch_step_n(const ModelDev<T> &M, const TaskDev &K, const StateDev<T> &S, const StepIO &io, StatsDev *stats,
-                                 cudaStream_t stream, bool lone) {
-    // the fp64 verification build keeps one (damped) instantiation; with zero damping its second factor equals the first
-    if (sizeof(T) == 8 || M.any_damping) return launch_step_nd<T, N, BLOCK, true>(M, K, S, io, stats, stream, lone);
-    if constexpr (sizeof(T) == 4) return launch_step_nd<T, N, BLOCK, false>(M, K, S, io, stats, stream, lone);
-    return cudaErrorInvalidValue;
-}
+namespace {
 
-template <typename T>
-cudaError_t launch_step(int n_dof, int n_contacts, int block, bool lone, const ModelDev<T> &M, const TaskDev &K,
-                        const StateDev<T> &S, const StepIO &io, StatsDev *stats, cudaStream_t stream) {
-    if (n_contacts != OS2R_NC) return cudaErrorInvalidValue;
-    if (sizeof(T) == 4 && block == OS2R_BLOCK_WIDE) {
-        if constexpr (sizeof(T) == 4) {
-            OS2R_DISPATCH_N(n_dof, return (launch_step_n<T, N_, OS2R_BLOCK_WIDE>(M, K, S, io, stats, stream, false)));
+struct StepFn {          // one instantiation of the step kernel
+    const void *fn;
+    size_t smem;
+    int envs_per_block;
+};
+
+template <typename V, int N, int BLOCK, bool DAMPED>
+StepFn step_fn() {
+    // two resident 7-warp blocks per SM for the float build (128 registers per thread); everything else: no occupancy target
+    constexpr int MINB = (VT<V>::LANES == 1 && sizeof(typename VT<V>::S) == 4 && BLOCK == OS2R_BLOCK_WIDE) ? 2 : 1;
+    return StepFn{(const void *)step_kernel<V, N, OS2R_NC, BLOCK, DAMPED, MINB>, step_smem_bytes<V, N, BLOCK>(), BLOCK * VT<V>::LANES};
+}
+template <typename V, int N, int BLOCK>
+StepFn step_fn_d(bool damped) {
+    // the fp64 verification build keeps one (damped) instantiation; with zero damping its second factor equals the first
+    if (sizeof(typename VT<V>::S) == 8 || damped) return step_fn<V, N, BLOCK, true>();
+    if constexpr (sizeof(typename VT<V>::S) == 4) return step_fn<V, N, BLOCK, false>();
+    return StepFn{nullptr, 0, 0};
+}
+template <typename V>
+cudaError_t pick(int n_dof, int block, bool damped, StepFn *out) {
+    if (block == OS2R_BLOCK_WIDE) {
+        if constexpr (sizeof(typename VT<V>::S) == 4) {
+            OS2R_DISPATCH_N(n_dof, *out = (step_fn_d<V, N_, OS2R_BLOCK_WIDE>(damped)));
+            return cudaSuccess;
         }
+        return cudaErrorInvalidValue;
     }
     if (block != OS2R_BLOCK) return cudaErrorInvalidValue;
-    OS2R_DISPATCH_N(n_dof, return (launch_step_n<T, N_, OS2R_BLOCK>(M, K, S, io, stats, stream, lone)));
-    return cudaErrorInvalidValue;
+    OS2R_DISPATCH_N(n_dof, *out = (step_fn_d<V, N_, OS2R_BLOCK>(damped)));
+    return cudaSuccess;
+}
+cudaError_t pick_build(int build, int n_dof, int block, bool damped, StepFn *out) {
+    switch (build) {
+    case OS2R_BUILD_PAIR: return pick<f2>(n_dof, block, damped, out);
+    case OS2R_BUILD_F32: return pick<float>(n_dof, block, damped, out);
+    case OS2R_BUILD_F64: return pick<double>(n_dof, block, true, out);
+    default: return cudaErrorInvalidValue;
+    }
+}
+
+}  // namespace
+
+template <typename T>
+cudaError_t launch_step(int build, int n_dof, int n_contacts, int block, const ModelDev<T> &M, const TaskDev &K,
+                        const StateDev<T> &S, const StepIO &io, StatsDev *stats, cudaStream_t stream) {
+    if (n_contacts != OS2R_NC) return cudaErrorInvalidValue;
+    if ((build == OS2R_BUILD_F64) != (sizeof(T) == 8)) return cudaErrorInvalidValue;
+    StepFn f;
+    cudaError_t e = pick_build(build, n_dof, block, M.any_damping != 0, &f);
+    if (e != cudaSuccess) return e;
+    // blocks that need more than 48 KB of dynamic shared memory were opted in by prepare_step (once per handle,
+    // on the handle's device: the attribute is per device, a process can hold handles on several GPUs)
+    void *args[] = {(void *)&M, (void *)&K, (void *)&S, (void *)&io, (void *)&stats};
+    return cudaLaunchKernel(f.fn, dim3(grid_for(S.n_envs, f.envs_per_block)), dim3(block), args, f.smem, stream);
 }
 
 template <typename T>
@@ -421,59 +495,30 @@ cudaError_t launch_init(const TaskDev &K, const StateDev<T> &S, double nominal_g
     return cudaGetLastError();
 }
 
-template <typename T, int N, int BLOCK, bool DAMPED>
-static cudaError_t step_attr_nd(cudaFuncAttributes *attr, int *blocks_per_sm) {
-    constexpr size_t smem = step_smem_bytes<T, N, BLOCK>();
-    cudaError_t e = cudaFuncGetAttributes(attr, step_kernel<T, N, OS2R_NC, BLOCK, DAMPED, false>);
-    if (e != cudaSuccess) return e;
-    if (smem > 48 * 1024) {
-        e = cudaFuncSetAttribute(step_kernel<T, N, OS2R_NC, BLOCK, DAMPED, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-    }
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, step_kernel<T, N, OS2R_NC, BLOCK, DAMPED, false>, BLOCK, smem);
-}
-template <typename T, int N, int BLOCK>
-static cudaError_t step_attr_n(bool damped, cudaFuncAttributes *attr, int *blocks_per_sm) {
-    if (sizeof(T) == 8 || damped) return step_attr_nd<T, N, BLOCK, true>(attr, blocks_per_sm);
-    if constexpr (sizeof(T) == 4) return step_attr_nd<T, N, BLOCK, false>(attr, blocks_per_sm);
-    return cudaErrorInvalidValue;
-}
-
-template <typename T>
-cudaError_t step_kernel_attributes(int n_dof, int block, bool damped, cudaFuncAttributes *attr, int *blocks_per_sm) {
-    if (sizeof(T) == 4 && block == OS2R_BLOCK_WIDE) {
-        if constexpr (sizeof(T) == 4) {
-            OS2R_DISPATCH_N(n_dof, return (step_attr_n<T, N_, OS2R_BLOCK_WIDE>(damped, attr, blocks_per_sm)));
-        }
-    }
-    OS2R_DISPATCH_N(n_dof, return (step_attr_n<T, N_, OS2R_BLOCK>(damped, attr, blocks_per_sm)));
-    return cudaErrorInvalidValue;
-}
-
-template <typename T, int N, int BLOCK, bool DAMPED>
-static cudaError_t prepare_nd() {
-    constexpr size_t smem = step_smem_bytes<T, N, BLOCK>();
-    if (smem <= 48 * 1024) return cudaSuccess;
-    return cudaFuncSetAttribute(step_kernel<T, N, OS2R_NC, BLOCK, DAMPED, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-}
-template <typename T, int N, int BLOCK>
-static cudaError_t prepare_n() {
-    cudaError_t e = prepare_nd<T, N, BLOCK, true>();
-    if (e != cudaSuccess) return e;
-    if constexpr (sizeof(T) == 4) return prepare_nd<T, N, BLOCK, false>();
-    return cudaSuccess;
-}
 // Opt the step kernels this handle can launch (damped and undamped build) into their dynamic shared memory size on the
 // CURRENT device. Called by os2r_create under its device guard.
-template <typename T>
-cudaError_t prepare_step(int n_dof, int block) {
-    if (sizeof(T) == 4 && block == OS2R_BLOCK_WIDE) {
-        if constexpr (sizeof(T) == 4) {
-            OS2R_DISPATCH_N(n_dof, return (prepare_n<T, N_, OS2R_BLOCK_WIDE>()));
+cudaError_t prepare_step(int build, int n_dof, int block) {
+    for (int damped = 0; damped < 2; ++damped) {
+        StepFn f;
+        cudaError_t e = pick_build(build, n_dof, block, damped != 0, &f);
+        if (e != cudaSuccess) return e;
+        if (f.smem > 48 * 1024) {
+            e = cudaFuncSetAttribute(f.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f.smem);
+            if (e != cudaSuccess) return e;
         }
     }
-    OS2R_DISPATCH_N(n_dof, return (prepare_n<T, N_, OS2R_BLOCK>()));
-    return cudaErrorInvalidValue;
+    return cudaSuccess;
+}
+
+cudaError_t step_kernel_attributes(int build, int n_dof, int block, bool damped, cudaFuncAttributes *attr,
+                                   int *blocks_per_sm, int *envs_per_block) {
+    StepFn f;
+    cudaError_t e = pick_build(build, n_dof, block, damped, &f);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncGetAttributes(attr, f.fn);
+    if (e != cudaSuccess) return e;
+    if (envs_per_block) *envs_per_block = f.envs_per_block;
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, f.fn, block, f.smem);
 }
 
 cudaError_t launch_fma_peak(float *out, int blocks, int iters, cudaStream_t stream) {
@@ -482,14 +527,11 @@ cudaError_t launch_fma_peak(float *out, int blocks, int iters, cudaStream_t stre
 }
 
 #define OS2R_INSTANTIATE(T)                                                                                   \
-    template int step_block_threads<T>(int64_t, int);                                                         \
-    template cudaError_t launch_step<T>(int, int, int, bool, const ModelDev<T> &, const TaskDev &, const StateDev<T> &, \
+    template cudaError_t launch_step<T>(int, int, int, int, const ModelDev<T> &, const TaskDev &, const StateDev<T> &, \
                                         const StepIO &, StatsDev *, cudaStream_t);                            \
     template cudaError_t launch_reset<T>(int, int, const TaskDev &, const StateDev<T> &, const uint8_t *,     \
                                          float *, cudaStream_t);                                              \
-    template cudaError_t launch_init<T>(const TaskDev &, const StateDev<T> &, double, cudaStream_t);          \
-    template cudaError_t step_kernel_attributes<T>(int, int, bool, cudaFuncAttributes *, int *);            \
-    template cudaError_t prepare_step<T>(int, int);
+    template cudaError_t launch_init<T>(const TaskDev &, const StateDev<T> &, double, cudaStream_t);
 OS2R_INSTANTIATE(float)
 OS2R_INSTANTIATE(double)
 

@@ -246,10 +246,10 @@ class Engine:
         return {name: getattr(s, name) for name, _ in _capi.Stats._fields_}
 
     def kernel_info(self) -> dict:
-        vals = [C.c_int32() for _ in range(5)]
+        vals = [C.c_int32() for _ in range(6)]
         _capi.check(self.lib.os2r_kernel_info(self.handle, *[C.byref(v) for v in vals]), self.lib)
         return dict(zip(('block_threads', 'grid_blocks', 'regs_per_thread', 'local_bytes_per_thread',
-                         'resident_blocks_per_sm'), (v.value for v in vals)))
+                         'resident_blocks_per_sm', 'envs_per_thread'), (v.value for v in vals)))
 
     @property
     def kernel_launches(self) -> int:

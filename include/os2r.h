@@ -170,11 +170,14 @@ int32_t os2r_create(const os2r_model *model, const os2r_task_cfg *task, int64_t 
 typedef struct os2r_tuning {
     double sort_margin;        /* ground clearance (m) below which a contact proxy counts as "near" for the lane sort;
                                   <= 0: default 0.002                                                              */
-    int32_t force_block;       /* threads per block of the step kernel; 0: chosen from the batch size            */
-    int32_t force_lone;        /* -1 / +1: force the build without / with an occupancy target off / on; 0: auto  */
+    int32_t force_block;       /* threads per block of the step kernel (64, or 224 for the fp32 builds); 0: chosen
+                                  from the batch size                                                             */
+    int32_t force_pair;        /* 1: the fp32 build that steps TWO envs per thread in packed fp32x2 registers
+                                  (FFMA2, sm_100); measured slower than the default one-env-per-thread build on
+                                  B200, kept for A/B runs. Agrees with the default build to
+                                  rounding, not bit for bit                                                       */
     int32_t disable_root_fold; /* 1: run the general per-body code for the yaw pivot (verification of the fold)  */
-    int32_t force_scalar;      /* 1: one env per thread even where the paired (two envs per thread, packed
-                                  f32x2) build would be chosen                                                    */
+    int32_t _pad;
 } os2r_tuning;
 /* os2r_create with explicit tuning (NULL = defaults = os2r_create). */
 int32_t os2r_create_tuned(const os2r_model *model, const os2r_task_cfg *task, int64_t n_envs,
@@ -274,7 +277,7 @@ int64_t os2r_kernel_launches(const os2r_env *env); /* kernels launched by this h
  * resident_blocks_per_sm comes from the CUDA occupancy API. Any out pointer may be NULL. */
 int32_t os2r_kernel_info(const os2r_env *env, int32_t *block_threads, int32_t *grid_blocks,
                          int32_t *regs_per_thread, int32_t *local_bytes_per_thread,
-                         int32_t *resident_blocks_per_sm);
+                         int32_t *resident_blocks_per_sm, int32_t *envs_per_thread);
 /* fp32 FMA-pipe peak microbenchmark on the handle's device: returns TFLOP/s (2 flop per FMA)
  * measured with CUDA events (MEASURED_PEAKS.json has no fp32 entry). */
 int32_t os2r_measure_fp32_peak(int32_t device, double *tflops_out, double *sm_clock_mhz_out);

@@ -55,6 +55,53 @@ __global__ void __launch_bounds__(256) rate_kernel(float *out, const float *in, 
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// MODE 4 / 5: scalar FFMA / packed FFMA2 whose three operands are DISTINCT registers that change from instruction to
+// instruction (no operand-reuse cache hits, register-bank conflicts as in real code): 8 independent accumulators.
+template <int MODE>
+__global__ void __launch_bounds__(256) mix_kernel(float *out, const float *in, int iters) {
+    float a[8], b[8], c[8];
+    unsigned long long pa[8], pb[8], pc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        a[k] = in[k] + threadIdx.x * 1e-6f; b[k] = in[8 + k]; c[k] = in[16 + k];
+        pa[k] = pack(a[k], a[k] * 0.5f); pb[k] = pack(b[k], b[k] * 0.5f); pc[k] = pack(c[k], c[k] * 0.5f);
+    }
+#pragma unroll 1
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                if (MODE == 4) c[k] = fmaf(a[(k + u) & 7], b[(k + 3 * u + 1) & 7], c[k]);
+                else pc[k] = fma2(pa[(k + u) & 7], pb[(k + 3 * u + 1) & 7], pc[k]);
+            }
+        }
+    }
+    float s = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += (MODE == 5) ? lo_of(pc[k]) : c[k];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+template <int MODE>
+void run_mix(const char *name, float *out, const float *in, int sms, double ghz, int threads) {
+    const int iters = 20000;
+    cudaEvent_t t0, t1;
+    cudaEventCreate(&t0); cudaEventCreate(&t1);
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; ++rep) {
+        cudaEventRecord(t0);
+        mix_kernel<MODE><<<sms, threads>>>(out, in, iters);
+        cudaEventRecord(t1);
+        cudaEventSynchronize(t1);
+        float ms; cudaEventElapsedTime(&ms, t0, t1);
+        if (rep && ms < best) best = ms;
+    }
+    const double cycles = best * 1e-3 * ghz * 1e9, instr_per_warp = 16.0 * 8 * iters, warps = threads / 32.0;
+    const double fma_per_instr = MODE == 5 ? 64.0 : 32.0;
+    printf("%-28s warps/SM %4.1f: cycles per warp-instr %6.3f  SM IPC %5.3f  FMA/clk/SM %6.1f\n", name, warps,
+           cycles / instr_per_warp, instr_per_warp * warps / cycles, instr_per_warp * warps * fma_per_instr / cycles);
+}
+
 template <int MODE, int ILP>
 void run(const char *name, float *out, const float *in, int sms, double ghz, int threads) {
     Consts K;
@@ -84,11 +131,19 @@ int main() {
     cudaDeviceProp p; cudaGetDeviceProperties(&p, 0);
     const double ghz = p.clockRate / 1e6;
     printf("%s, %d SMs, %.3f GHz\n", p.name, p.multiProcessorCount, ghz);
-    float *out, *in; cudaMalloc(&out, 1 << 24); cudaMalloc(&in, 64);
+    float *out, *in; cudaMalloc(&out, 1 << 24); cudaMalloc(&in, 256);
     const float h[4] = {0.999f, 1e-3f, 0.998f, 2e-3f};
     cudaMemcpy(in, h, sizeof(h), cudaMemcpyHostToDevice);
     const int sms = p.multiProcessorCount;
-    const int shapes[] = {32, 128, 224, 448, 1024};
+    float hin[24];
+    for (int i = 0; i < 24; ++i) hin[i] = 0.5f + 0.01f * i;
+    cudaMemcpy(in, hin, sizeof(hin), cudaMemcpyHostToDevice);
+    for (int threads : {32, 64, 128, 224, 256}) {
+        run_mix<4>("FFMA distinct operands", out, in, sms, ghz, threads);
+        run_mix<5>("FFMA2 distinct operands", out, in, sms, ghz, threads);
+    }
+    cudaMemcpy(in, h, sizeof(h), cudaMemcpyHostToDevice);
+    const int shapes[] = {32, 224};
     for (int threads : shapes) {
         run<0, 1>("FFMA reg", out, in, sms, ghz, threads);
         run<0, 2>("FFMA reg", out, in, sms, ghz, threads);
