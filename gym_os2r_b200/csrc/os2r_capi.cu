@@ -152,7 +152,7 @@ struct os2r_env {
     uint8_t *cls = nullptr;
     StatsDev *stats = nullptr;
     int sm_count = 0;
-    int build = OS2R_BUILD_F32;      // which step kernel: fp32 one env per thread (product), fp32 pairs (opt-in), fp64
+    int build = OS2R_BUILD_F32;      // which step kernel: fp32 (product) or fp64 (verification)
     int block = OS2R_BLOCK;          // threads per block of the step kernel for this batch size
     StateDev<float> s32;
     StateDev<double> s64;
@@ -367,7 +367,7 @@ int32_t os2r_create_tuned(const os2r_model *model, const os2r_task_cfg *task, in
 
     os2r_env *h = new os2r_env();
     h->sm_count = sm_count;
-    h->build = precision == 64 ? OS2R_BUILD_F64 : (tune.force_pair ? OS2R_BUILD_PAIR : OS2R_BUILD_F32);
+    h->build = precision == 64 ? OS2R_BUILD_F64 : OS2R_BUILD_F32;
     h->block = step_block_threads(h->build, n_envs, sm_count);
     if (tune.force_block == OS2R_BLOCK || (precision == 32 && tune.force_block == OS2R_BLOCK_WIDE)) h->block = tune.force_block;
     else if (tune.force_block != 0) { delete h; return fail("os2r_create: tuning.force_block %d unsupported (%d, or %d for the fp32 builds)", tune.force_block, OS2R_BLOCK, OS2R_BLOCK_WIDE); }

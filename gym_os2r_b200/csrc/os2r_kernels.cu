@@ -155,11 +155,11 @@ __device__ __forceinline__ V from_halves(const float (&x)[VT<V>::LANES]) {
 //     per SM (MINB = 2: 128 registers per thread; 65 536 envs = 293 blocks = ONE wave of 14 warps per SM); smaller
 //     batches run 2-warp blocks without an occupancy target (MINB = 1: ptxas takes ~200-225 registers and schedules for
 //     instruction-level parallelism — with one or two warps per scheduler a warp is bound by its own dependency chains);
-// V = double: the fp64 verification build, one env per thread;
-// V = f2    : TWO envs per thread through the packed fp32x2 instructions of sm_100 (FFMA2 / FMUL2 / FADD2), one block
-//     per SM at up to 255 registers per thread. Measured slower than the float build on this latency-bound kernel
-//      and therefore opt-in (os2r_tuning.force_pair); results agree with the float build to
-//     rounding but are not bit-identical (ptxas contracts packed mul + add pairs on its own).
+// V = double: the fp64 verification build, one env per thread.
+// (The kernel is written for LANES envs per thread; a build with V = f2, TWO envs per thread in packed fp32x2 registers
+// and one block per SM at 255 registers, was measured in round 2 — 106 vs 89 us per step, profiles/r2_step_kernel_pair_*
+// — and dropped: with 7 warps per SM the kernel is bound by dependent-issue latency, not by issue slots. The packed
+// instructions are used INSIDE an env instead: os2r_device.cuh, forward pass.)
 template <typename V, int N, int NC, int BLOCK, bool DAMPED, int MINB>
 __global__ void __launch_bounds__(BLOCK, MINB)
 step_kernel(const __grid_constant__ ModelDev<typename VT<V>::S> M, const __grid_constant__ TaskDev K,
@@ -414,11 +414,10 @@ static constexpr size_t step_smem_bytes() {
 }
 
 // Threads per block of the step kernel for a batch. Wide blocks (7 warps) give the lane sort enough envs to fill whole
-// warps with one contact class; they need about one block per SM to pay off (float: 224 envs per block, pair build: 448).
+// warps with one contact class; they need about one block per SM to pay off.
 // Small batches and the fp64 verification build keep 2-warp blocks (more SMs busy).
 int step_block_threads(int build, int64_t n_envs, int sm_count) {
     if (build == OS2R_BUILD_F32 && n_envs >= (int64_t)sm_count * OS2R_BLOCK_WIDE) return OS2R_BLOCK_WIDE;
-    if (build == OS2R_BUILD_PAIR && n_envs * 8 >= (int64_t)sm_count * OS2R_BLOCK_WIDE * 2 * 7) return OS2R_BLOCK_WIDE;
     return OS2R_BLOCK;
 }
 
@@ -458,7 +457,6 @@ cudaError_t pick(int n_dof, int block, bool damped, StepFn *out) {
 }
 cudaError_t pick_build(int build, int n_dof, int block, bool damped, StepFn *out) {
     switch (build) {
-    case OS2R_BUILD_PAIR: return pick<f2>(n_dof, block, damped, out);
     case OS2R_BUILD_F32: return pick<float>(n_dof, block, damped, out);
     case OS2R_BUILD_F64: return pick<double>(n_dof, block, true, out);
     default: return cudaErrorInvalidValue;

@@ -18,7 +18,6 @@
 
 // builds of the step kernel
 #define OS2R_BUILD_F32 0    // fp32, one env per thread: the product path
-#define OS2R_BUILD_PAIR 1   // fp32, two envs per thread in packed fp32x2 registers (opt-in: os2r_tuning.force_pair)
 #define OS2R_BUILD_F64 2    // fp64, one env per thread (verification)
 
 namespace os2r {

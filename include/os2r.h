@@ -172,10 +172,7 @@ typedef struct os2r_tuning {
                                   <= 0: default 0.002                                                              */
     int32_t force_block;       /* threads per block of the step kernel (64, or 224 for the fp32 builds); 0: chosen
                                   from the batch size                                                             */
-    int32_t force_pair;        /* 1: the fp32 build that steps TWO envs per thread in packed fp32x2 registers
-                                  (FFMA2, sm_100); measured slower than the default one-env-per-thread build on
-                                  B200, kept for A/B runs. Agrees with the default build to
-                                  rounding, not bit for bit                                                       */
+    int32_t _reserved0;
     int32_t disable_root_fold; /* 1: run the general per-body code for the yaw pivot (verification of the fold)  */
     int32_t _pad;
 } os2r_tuning;

@@ -95,62 +95,6 @@ def test_single_step_parity(mode, contact):
         eng.close()
 
 
-@pytest.mark.parametrize('mode', ['simple', 'fixed', 'fixed_hip', 'free_hip'])
-@pytest.mark.parametrize('N', [333, 148 * 448])
-def test_pair_build_agrees_with_the_oracle_and_the_default_build(mode, N):
-    """The opt-in fp32 build that steps TWO envs per thread in packed fp32x2 registers (FFMA2; os2r_tuning.force_pair):
-    same physics, same per-env sweep exit (a finished env is frozen while its thread partner sweeps on), odd batch
-    sizes leave a half-filled thread. Against the fp64 oracle it meets the bounds of the default build; against the
-    default build it agrees to fp32 rounding (not bit for bit: ptxas contracts packed mul + add pairs on its own)."""
-    rng = np.random.RandomState(17)
-    contact = mode != 'simple'
-    task, cm, cfg = make_config(mode, reward=_reward_for(mode), pgs_tol=1e-6, auto_reset=True, max_episode_steps=3,
-                                reset_randomized=mode in ('fixed_hip', 'free_hip'), randomize_params=True)
-    n = cm.n_dof
-    st = _random_state(cm, N, rng, contact)
-    acts = [rng.uniform(-1, 1, (N, 2)).astype(np.float32) for _ in range(4)]
-    outs = []
-    for tuning in ({'force_pair': 1}, None):
-        eng = Engine(cm, cfg, N, seed=9, tuning=tuning)
-        assert eng.kernel_info()['envs_per_thread'] == (2 if tuning else 1)
-        eng.reset()
-        par = eng.get_params()
-        eng.set_state(st)
-        res = []
-        for t, a in enumerate(acts):        # step 3 hits the TimeLimit: auto-reset + parameter draws inside the kernel
-            obs, rew, done, info = eng.step(torch.as_tensor(a, device='cuda'))
-            res.append((eng.get_state(), obs.cpu().numpy().copy(), rew.cpu().numpy().copy(), done.cpu().numpy().copy(),
-                        info.cpu().numpy().copy()))
-        outs.append(res)
-        eng.close()
-    orc = oracle.Oracle(cm.struct, cfg, N, seed=9, nthreads=16)
-    orc.reset()
-    orc.params[:] = par
-    orc.state[:] = outs[0][0][0] * 0 + Engine_state_roundtrip(st)
-    o_o, r_o, d_o, _, _ = orc.step(acts[0].astype(np.float64))
-    for k, name in ((0, 'pair'), (1, 'default')):
-        sg = outs[k][0][0]
-        eq = np.abs(sg[:, :n] - orc.state[:, :n]).max(1)
-        ev = np.abs(sg[:, n:2 * n] - orc.state[:, n:2 * n]).max(1)
-        assert np.median(eq) < 5e-7 and np.median(ev) < 5e-4, (name, mode, np.median(eq), np.median(ev))
-        assert np.quantile(eq, 0.95) < 1e-5 and np.quantile(ev, 0.95) < 1e-2, (name, mode)
-    for t in range(len(acts)):
-        (sa, oa, ra, da, ia), (sb, ob, rb, db, ib) = outs[0][t], outs[1][t]
-        same = np.abs(sa[:, :2 * n] - sb[:, :2 * n]).max(1) < 1e-3          # envs whose contact set did not flip
-        assert same.mean() > 0.97, (mode, t, same.mean())
-        assert np.median(np.abs(sa[:, :n] - sb[:, :n]).max(1)) < 1e-6, (mode, t)
-        assert np.array_equal(da[same], db[same]) and np.array_equal(ia[same], ib[same]), (mode, t)
-        np.testing.assert_allclose(oa[same], ob[same], atol=2e-3)
-    assert outs[0][2][3].all() and outs[1][2][3].all()                       # the TimeLimit step reset every env
-
-
-def Engine_state_roundtrip(st):
-    """what os2r_set_state keeps of a double state in the fp32 build: hi + lo float pairs (exact to ~1e-14)"""
-    hi = st.astype(np.float32).astype(np.float64)
-    lo = (st - hi).astype(np.float32).astype(np.float64)
-    return hi + lo
-
-
 def test_damping_written_through_set_params_is_implicit():
     """fixed_hip carries no joint damping, so its step kernel is the instantiation without the second (implicit
     damping) factorisation; a damping written through os2r_set_params must switch to the damped one and match the

@@ -7,7 +7,6 @@ pool) in the contact steady state and in the contact-free window after a reset.
       cfg4    free_hip 65 536 / 131 072 envs (BASELINE config 4)
       small   N = 32 .. 32 768
       modes   fixed / simple
-      pair    `std` with tuning force_pair=1 (two envs per thread, packed fp32x2) beside the default build
 A variant library built with other -D flags is selected with OS2R_LIB=/path/to/lib.so; scheduling knobs travel in the
 os2r_tuning struct (Engine(tuning=...)), never through the environment."""
 import os
@@ -91,8 +90,6 @@ if __name__ == '__main__':
     for which in cases:
         if which == 'std':
             P(steady()); P(fresh())
-        if which == 'pair':
-            P(steady(tuning={'force_pair': 1})); P(fresh(tuning={'force_pair': 1}))
         if which == 'cfg4':
             P(steady(mode='free_hip')); P(steady(mode='free_hip', N=131072, pre=800)); P(fresh(mode='free_hip'))
         if which == 'small':

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Workload for compute-sanitizer (tools/sanitize.sh): every n_dof (task modes simple / fixed / fixed_hip / free_hip),
 2 048 envs (+ a ragged 2 048 + 37 batch), 50 env steps with contacts, randomizers, TimeLimit auto-resets, the packed
-host step and both fp32 builds, the wide lane-sorted blocks included (forced: the batch is far below their threshold)."""
+host step, the wide lane-sorted blocks included (forced: the batch is far below their threshold)."""
 import os
 import sys
 
@@ -20,8 +20,7 @@ for mode in ('simple', 'fixed', 'fixed_hip', 'free_hip'):
     task, cm, cfg = make_config(mode, reward=reward, reset_positions=('ground', 'lay', 'stand'), auto_reset=True,
                                 max_episode_steps=20, reset_randomized=mode in ('fixed_hip', 'free_hip'),
                                 randomize_params=True, randomize_gravity=True, pgs_tol=1e-6)
-    for N, tuning in ((2048, None), (2048 + 37, {'force_block': 224}), (2048 + 37, {'force_pair': 1, 'force_block': 224}),
-                      (333, {'force_pair': 1})):
+    for N, tuning in ((2048, None), (2048 + 37, {'force_block': 224}), (333, {'force_block': 64})):
         eng = Engine(cm, cfg, N, seed=3, tuning=tuning)
         eng.reset()
         rng = np.random.RandomState(0)
