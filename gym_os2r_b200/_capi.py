@@ -139,6 +139,7 @@ SYMBOLS = {
     'os2r_kernel_launches': (C.c_int64, [_vp]),
     'os2r_kernel_info': (_i32, [_vp, C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32),
                                 C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32)]),
+    'os2r_debug_counters': (_i32, [_i32, C.POINTER(C.c_uint64), _i32]),
     'os2r_measure_fp32_peak': (_i32, [_i32, C.POINTER(_f64), C.POINTER(_f64)]),
 }
 

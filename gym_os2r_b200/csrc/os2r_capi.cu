@@ -345,7 +345,8 @@ int32_t os2r_create_tuned(const os2r_model *model, const os2r_task_cfg *task, in
     *out = nullptr;
     if (n_envs <= 0) return fail("os2r_create: n_envs must be positive (got %lld)", (long long)n_envs);
     if (model->n_dof < 2 || model->n_dof > OS2R_MAX_DOF) return fail("os2r_create: n_dof %d unsupported (2..5)", model->n_dof);
-    if (model->n_contacts != OS2R_NC) return fail("os2r_create: n_contacts %d unsupported (kernels are built for %d proxies)", model->n_contacts, OS2R_NC);
+    if (!supported_shape(model->n_dof, model->n_contacts))
+        return fail("os2r_create: no kernel is built for %d moving joints with %d contact proxies (built: 2..5 joints with 3 proxies, 5 joints with 4)", model->n_dof, model->n_contacts);
     if (precision != 32 && precision != 64) return fail("os2r_create: precision must be 32 or 64");
     if (!(model->pgs_tol >= 0.0)) return fail("os2r_create: pgs_tol must be >= 0");
     if (task->obs_dim <= 0 || task->obs_dim > OS2R_MAX_OBS) return fail("os2r_create: obs_dim %d out of range", task->obs_dim);
@@ -399,7 +400,7 @@ int32_t os2r_create_tuned(const os2r_model *model, const os2r_task_cfg *task, in
     if ((e = cudaMalloc(&h->cls, n_envs)) != cudaSuccess) return cleanup("cudaMalloc(cls)", e);
     if ((e = cudaMalloc(&h->stats, sizeof(StatsDev))) != cudaSuccess) return cleanup("cudaMalloc(stats)", e);
     if ((e = cudaMemset(h->stats, 0, sizeof(StatsDev))) != cudaSuccess) return cleanup("cudaMemset(stats)", e);
-    e = prepare_step(h->build, model->n_dof, h->block);
+    e = prepare_step(h->build, model->n_dof, model->n_contacts, h->block);
     if (e != cudaSuccess) return cleanup("cudaFuncSetAttribute(step kernel shared memory)", e);
     if (precision == 32) { carve<float>(h, h->s32); e = launch_init<float>(h->taskdev, h->s32, model->gravity_z, 0); }
     else { carve<double>(h, h->s64); e = launch_init<double>(h->taskdev, h->s64, model->gravity_z, 0); }
@@ -717,7 +718,7 @@ int32_t os2r_kernel_info(const os2r_env *h, int32_t *block_threads, int32_t *gri
     DeviceGuard guard(h->device);
     cudaFuncAttributes a;
     int resident = 0, epb = h->block;
-    cudaError_t e = step_kernel_attributes(h->build, h->model.n_dof, h->block, h->m32.any_damping != 0, &a, &resident, &epb);
+    cudaError_t e = step_kernel_attributes(h->build, h->model.n_dof, h->model.n_contacts, h->block, h->m32.any_damping != 0, &a, &resident, &epb);
     if (e != cudaSuccess) return fail("cudaFuncGetAttributes failed: %s", cudaGetErrorString(e));
     if (block_threads) *block_threads = h->block;
     if (grid_blocks) *grid_blocks = (int32_t)((h->n + epb - 1) / epb);
@@ -725,6 +726,19 @@ int32_t os2r_kernel_info(const os2r_env *h, int32_t *block_threads, int32_t *gri
     if (regs_per_thread) *regs_per_thread = a.numRegs;
     if (local_bytes_per_thread) *local_bytes_per_thread = (int32_t)a.localSizeBytes;
     if (resident_blocks_per_sm) *resident_blocks_per_sm = resident;
+    return 0;
+}
+
+int32_t os2r_debug_counters(int32_t device, uint64_t *out8, int32_t clear) {
+    if (!out8) return fail("os2r_debug_counters: null argument");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return fail("os2r_debug_counters: no such CUDA device %d", device);
+    DeviceGuard guard(device);
+    CK(cudaDeviceSynchronize());
+    unsigned long long tmp[8];
+    cudaError_t e = read_check_counters(tmp, clear != 0);
+    if (e != cudaSuccess) return fail("os2r_debug_counters: %s", cudaGetErrorString(e));
+    for (int i = 0; i < 8; ++i) out8[i] = tmp[i];
     return 0;
 }
 

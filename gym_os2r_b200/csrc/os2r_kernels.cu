@@ -5,6 +5,19 @@
 
 namespace os2r {
 
+// Checked build (-DOS2R_CHECKED, `make libos2r_checked.so`, tools/sanitize.sh): compute-sanitizer is closed on this
+// GPU pool, so the step kernel carries its own bounds / permutation checks; violations are COUNTED (a trap would take
+// the context down) and read back through os2r_debug_counters.
+//   [0] sorted source slot outside the block's window      [1] lane sort did not produce a permutation
+//   [2] env index outside the batch                        [3] terminal-record list overflowed its capacity
+//   [4] cold-slot guard word overwritten                   [7] 1 = this library was built with the checks
+__device__ unsigned long long g_check[8];
+#ifdef OS2R_CHECKED
+#define OS2R_CHECK(cond, k) do { if (!(cond)) atomicAdd(&g_check[k], 1ull); } while (0)
+#else
+#define OS2R_CHECK(cond, k) do { } while (0)
+#endif
+
 // ------------------------------------------------------------------------------------------------
 // reset of one env, written straight to the SoA state (rare path, fp64 draws shared with the oracle)
 // ------------------------------------------------------------------------------------------------
@@ -208,6 +221,21 @@ step_kernel(const __grid_constant__ ModelDev<typename VT<V>::S> M, const __grid_
     }
     int src[LANES];
     sorted_sources<BLOCK, LANES, (1 << NC) + 1>(key, src, reinterpret_cast<int *>(smem_raw));
+#ifdef OS2R_CHECKED
+    {   // the sort must hand every window slot to exactly one thread
+        __shared__ int owner[EPB];
+#pragma unroll
+        for (int h = 0; h < LANES; ++h) {
+            OS2R_CHECK(src[h] >= 0 && src[h] < EPB, 0);
+            if (src[h] >= 0 && src[h] < EPB) owner[src[h]] = LANES * threadIdx.x + h;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int h = 0; h < LANES; ++h)
+            if (src[h] >= 0 && src[h] < EPB) OS2R_CHECK(owner[src[h]] == LANES * (int)threadIdx.x + h, 1);
+        __syncthreads();
+    }
+#endif
     int64_t e[LANES];
     bool valid[LANES];
 #pragma unroll
@@ -215,6 +243,7 @@ step_kernel(const __grid_constant__ ModelDev<typename VT<V>::S> M, const __grid_
         const int64_t e_raw = window + src[h];
         valid[h] = e_raw < NE;
         e[h] = valid[h] ? e_raw : NE - 1;
+        OS2R_CHECK(e[h] >= 0 && e[h] < NE, 2);
     }
     const Cold<V, BLOCK> C{reinterpret_cast<V *>(smem_raw) + threadIdx.x};
 
@@ -275,6 +304,9 @@ step_kernel(const __grid_constant__ ModelDev<typename VT<V>::S> M, const __grid_
     C(SL::ACT) = act_x;
     C(SL::ACT + 1) = act_y;
     C(SL::AFIN) = from_halves<V>(afin_);
+#ifdef OS2R_CHECKED
+    C(SL::COUNT) = V(12345.0f);          // guard word behind the last slot (the checked build allocates one more slot)
+#endif
 
 #pragma unroll 1
     for (int s = 0; s < M.substeps; ++s) {
@@ -283,6 +315,9 @@ step_kernel(const __grid_constant__ ModelDev<typename VT<V>::S> M, const __grid_
         __syncthreads();
         physics_iteration<V, N, NC, DAMPED, Cold<V, BLOCK>>(M, E, C);
     }
+#ifdef OS2R_CHECKED
+    OS2R_CHECK(half_of(C(SL::COUNT), 0) == (T)12345.0f, 4);
+#endif
     // ---- epilogue (fp64, once per ENV): the hot registers are parked next to the cold slots and every env of the
     //      thread is finished from shared memory, one after the other, by the same (rolled) code
 #pragma unroll
@@ -328,6 +363,7 @@ step_kernel(const __grid_constant__ ModelDev<typename VT<V>::S> M, const __grid_
 
         if (cause && IO.term_count) {
             const int k = atomicAdd(IO.term_count, 1);
+            OS2R_CHECK(k < IO.term_cap, 3);
             if (k < IO.term_cap) {
                 int32_t *rec = IO.term_records + (int64_t)k * (D + 2);
                 rec[0] = (int32_t)en;
@@ -395,20 +431,32 @@ __global__ void __launch_bounds__(256) fma_peak_kernel(float *out, int iters, fl
 // ------------------------------------------------------------------------------------------------
 static inline int grid_for(int64_t n, int per_block) { return (int)((n + per_block - 1) / per_block); }
 
-#define OS2R_DISPATCH_N(n_dof, CALL)                 \
-    switch (n_dof) {                                 \
-    case 2: { constexpr int N_ = 2; CALL; } break;   \
-    case 3: { constexpr int N_ = 3; CALL; } break;   \
-    case 4: { constexpr int N_ = 4; CALL; } break;   \
-    case 5: { constexpr int N_ = 5; CALL; } break;   \
-    default: return cudaErrorInvalidValue;           \
+// (moving joints, contact proxies) combinations the kernels are instantiated for: the shipped models carry the three
+// leg proxies (hip, knee, foot); the free-hip model `monopod` adds a fourth on the hip bracket (hip_link), which its free
+// boom_connector joint can swing into the ground. (5, 3) stays available for models compiled without it.
+#define OS2R_DISPATCH(n_dof, n_contacts, CALL)                                          \
+    switch ((n_dof) * 16 + (n_contacts)) {                                              \
+    case 2 * 16 + 3: { constexpr int N_ = 2, NC_ = 3; CALL; } break;                    \
+    case 3 * 16 + 3: { constexpr int N_ = 3, NC_ = 3; CALL; } break;                    \
+    case 4 * 16 + 3: { constexpr int N_ = 4, NC_ = 3; CALL; } break;                    \
+    case 5 * 16 + 3: { constexpr int N_ = 5, NC_ = 3; CALL; } break;                    \
+    case 5 * 16 + 4: { constexpr int N_ = 5, NC_ = 4; CALL; } break;                    \
+    default: return cudaErrorInvalidValue;                                              \
     }
+bool supported_shape(int n_dof, int n_contacts) {
+    auto probe = [&]() -> cudaError_t { OS2R_DISPATCH(n_dof, n_contacts, (void)N_; (void)NC_); return cudaSuccess; };
+    return probe() == cudaSuccess;
+}
 
-template <typename V, int N, int BLOCK>
+template <typename V, int N, int NC, int BLOCK>
 static constexpr size_t step_smem_bytes() {
     constexpr int LANES = VT<V>::LANES;
-    constexpr int NKEYS = (1 << OS2R_NC) + 1;
-    size_t cold = (size_t)ColdSlots<N, OS2R_NC>::COUNT * BLOCK * sizeof(V);
+    constexpr int NKEYS = (1 << NC) + 1;
+#ifdef OS2R_CHECKED
+    size_t cold = (size_t)(ColdSlots<N, NC>::COUNT + 1) * BLOCK * sizeof(V);     // + the guard slot
+#else
+    size_t cold = (size_t)ColdSlots<N, NC>::COUNT * BLOCK * sizeof(V);
+#endif
     size_t sort = (size_t)(((NKEYS * (BLOCK / 32) * LANES + 31) / 32) * 32 + BLOCK * LANES) * sizeof(int);
     return cold > sort ? cold : sort;
 }
@@ -429,36 +477,36 @@ struct StepFn {          // one instantiation of the step kernel
     int envs_per_block;
 };
 
-template <typename V, int N, int BLOCK, bool DAMPED>
+template <typename V, int N, int NC, int BLOCK, bool DAMPED>
 StepFn step_fn() {
     // two resident 7-warp blocks per SM for the float build (128 registers per thread); everything else: no occupancy target
     constexpr int MINB = (VT<V>::LANES == 1 && sizeof(typename VT<V>::S) == 4 && BLOCK == OS2R_BLOCK_WIDE) ? 2 : 1;
-    return StepFn{(const void *)step_kernel<V, N, OS2R_NC, BLOCK, DAMPED, MINB>, step_smem_bytes<V, N, BLOCK>(), BLOCK * VT<V>::LANES};
+    return StepFn{(const void *)step_kernel<V, N, NC, BLOCK, DAMPED, MINB>, step_smem_bytes<V, N, NC, BLOCK>(), BLOCK * VT<V>::LANES};
 }
-template <typename V, int N, int BLOCK>
+template <typename V, int N, int NC, int BLOCK>
 StepFn step_fn_d(bool damped) {
     // the fp64 verification build keeps one (damped) instantiation; with zero damping its second factor equals the first
-    if (sizeof(typename VT<V>::S) == 8 || damped) return step_fn<V, N, BLOCK, true>();
-    if constexpr (sizeof(typename VT<V>::S) == 4) return step_fn<V, N, BLOCK, false>();
+    if (sizeof(typename VT<V>::S) == 8 || damped) return step_fn<V, N, NC, BLOCK, true>();
+    if constexpr (sizeof(typename VT<V>::S) == 4) return step_fn<V, N, NC, BLOCK, false>();
     return StepFn{nullptr, 0, 0};
 }
 template <typename V>
-cudaError_t pick(int n_dof, int block, bool damped, StepFn *out) {
+cudaError_t pick(int n_dof, int n_contacts, int block, bool damped, StepFn *out) {
     if (block == OS2R_BLOCK_WIDE) {
         if constexpr (sizeof(typename VT<V>::S) == 4) {
-            OS2R_DISPATCH_N(n_dof, *out = (step_fn_d<V, N_, OS2R_BLOCK_WIDE>(damped)));
+            OS2R_DISPATCH(n_dof, n_contacts, *out = (step_fn_d<V, N_, NC_, OS2R_BLOCK_WIDE>(damped)));
             return cudaSuccess;
         }
         return cudaErrorInvalidValue;
     }
     if (block != OS2R_BLOCK) return cudaErrorInvalidValue;
-    OS2R_DISPATCH_N(n_dof, *out = (step_fn_d<V, N_, OS2R_BLOCK>(damped)));
+    OS2R_DISPATCH(n_dof, n_contacts, *out = (step_fn_d<V, N_, NC_, OS2R_BLOCK>(damped)));
     return cudaSuccess;
 }
-cudaError_t pick_build(int build, int n_dof, int block, bool damped, StepFn *out) {
+cudaError_t pick_build(int build, int n_dof, int n_contacts, int block, bool damped, StepFn *out) {
     switch (build) {
-    case OS2R_BUILD_F32: return pick<float>(n_dof, block, damped, out);
-    case OS2R_BUILD_F64: return pick<double>(n_dof, block, true, out);
+    case OS2R_BUILD_F32: return pick<float>(n_dof, n_contacts, block, damped, out);
+    case OS2R_BUILD_F64: return pick<double>(n_dof, n_contacts, block, true, out);
     default: return cudaErrorInvalidValue;
     }
 }
@@ -468,10 +516,9 @@ cudaError_t pick_build(int build, int n_dof, int block, bool damped, StepFn *out
 template <typename T>
 cudaError_t launch_step(int build, int n_dof, int n_contacts, int block, const ModelDev<T> &M, const TaskDev &K,
                         const StateDev<T> &S, const StepIO &io, StatsDev *stats, cudaStream_t stream) {
-    if (n_contacts != OS2R_NC) return cudaErrorInvalidValue;
     if ((build == OS2R_BUILD_F64) != (sizeof(T) == 8)) return cudaErrorInvalidValue;
     StepFn f;
-    cudaError_t e = pick_build(build, n_dof, block, M.any_damping != 0, &f);
+    cudaError_t e = pick_build(build, n_dof, n_contacts, block, M.any_damping != 0, &f);
     if (e != cudaSuccess) return e;
     // blocks that need more than 48 KB of dynamic shared memory were opted in by prepare_step (once per handle,
     // on the handle's device: the attribute is per device, a process can hold handles on several GPUs)
@@ -482,8 +529,7 @@ cudaError_t launch_step(int build, int n_dof, int n_contacts, int block, const M
 template <typename T>
 cudaError_t launch_reset(int n_dof, int n_contacts, const TaskDev &K, const StateDev<T> &S, const uint8_t *mask,
                          float *obs, cudaStream_t stream) {
-    if (n_contacts != OS2R_NC) return cudaErrorInvalidValue;
-    OS2R_DISPATCH_N(n_dof, (reset_kernel<T, N_, OS2R_NC><<<grid_for(S.n_envs, OS2R_BLOCK), OS2R_BLOCK, 0, stream>>>(K, S, mask, obs)));
+    OS2R_DISPATCH(n_dof, n_contacts, (reset_kernel<T, N_, NC_><<<grid_for(S.n_envs, OS2R_BLOCK), OS2R_BLOCK, 0, stream>>>(K, S, mask, obs)));
     return cudaGetLastError();
 }
 
@@ -495,10 +541,10 @@ cudaError_t launch_init(const TaskDev &K, const StateDev<T> &S, double nominal_g
 
 // Opt the step kernels this handle can launch (damped and undamped build) into their dynamic shared memory size on the
 // CURRENT device. Called by os2r_create under its device guard.
-cudaError_t prepare_step(int build, int n_dof, int block) {
+cudaError_t prepare_step(int build, int n_dof, int n_contacts, int block) {
     for (int damped = 0; damped < 2; ++damped) {
         StepFn f;
-        cudaError_t e = pick_build(build, n_dof, block, damped != 0, &f);
+        cudaError_t e = pick_build(build, n_dof, n_contacts, block, damped != 0, &f);
         if (e != cudaSuccess) return e;
         if (f.smem > 48 * 1024) {
             e = cudaFuncSetAttribute(f.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f.smem);
@@ -508,15 +554,30 @@ cudaError_t prepare_step(int build, int n_dof, int block) {
     return cudaSuccess;
 }
 
-cudaError_t step_kernel_attributes(int build, int n_dof, int block, bool damped, cudaFuncAttributes *attr,
+cudaError_t step_kernel_attributes(int build, int n_dof, int n_contacts, int block, bool damped, cudaFuncAttributes *attr,
                                    int *blocks_per_sm, int *envs_per_block) {
     StepFn f;
-    cudaError_t e = pick_build(build, n_dof, block, damped, &f);
+    cudaError_t e = pick_build(build, n_dof, n_contacts, block, damped, &f);
     if (e != cudaSuccess) return e;
     e = cudaFuncGetAttributes(attr, f.fn);
     if (e != cudaSuccess) return e;
     if (envs_per_block) *envs_per_block = f.envs_per_block;
     return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, f.fn, block, f.smem);
+}
+
+cudaError_t read_check_counters(unsigned long long out[8], bool clear) {
+    cudaError_t e = cudaMemcpyFromSymbol(out, g_check, 8 * sizeof(unsigned long long));
+    if (e != cudaSuccess) return e;
+#ifdef OS2R_CHECKED
+    out[7] = 1;
+#else
+    out[7] = 0;
+#endif
+    if (clear) {
+        const unsigned long long zero[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        e = cudaMemcpyToSymbol(g_check, zero, sizeof(zero));
+    }
+    return e;
 }
 
 cudaError_t launch_fma_peak(float *out, int blocks, int iters, cudaStream_t stream) {

@@ -12,9 +12,6 @@
 #ifndef OS2R_BLOCK_WIDE
 #define OS2R_BLOCK_WIDE 224
 #endif
-#ifndef OS2R_NC
-#define OS2R_NC 3
-#endif
 
 // builds of the step kernel
 #define OS2R_BUILD_F32 0    // fp32, one env per thread: the product path
@@ -31,9 +28,11 @@ cudaError_t launch_reset(int n_dof, int n_contacts, const TaskDev &K, const Stat
                          float *obs, cudaStream_t stream);
 template <typename T>
 cudaError_t launch_init(const TaskDev &K, const StateDev<T> &S, double nominal_gz, cudaStream_t stream);
-cudaError_t prepare_step(int build, int n_dof, int block);
-cudaError_t step_kernel_attributes(int build, int n_dof, int block, bool damped, cudaFuncAttributes *attr,
+cudaError_t prepare_step(int build, int n_dof, int n_contacts, int block);
+bool supported_shape(int n_dof, int n_contacts);
+cudaError_t step_kernel_attributes(int build, int n_dof, int n_contacts, int block, bool damped, cudaFuncAttributes *attr,
                                    int *blocks_per_sm, int *envs_per_block);
+cudaError_t read_check_counters(unsigned long long out[8], bool clear);
 cudaError_t launch_fma_peak(float *out, int blocks, int iters, cudaStream_t stream);
 
 }  // namespace os2r

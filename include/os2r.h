@@ -275,6 +275,11 @@ int64_t os2r_kernel_launches(const os2r_env *env); /* kernels launched by this h
 int32_t os2r_kernel_info(const os2r_env *env, int32_t *block_threads, int32_t *grid_blocks,
                          int32_t *regs_per_thread, int32_t *local_bytes_per_thread,
                          int32_t *resident_blocks_per_sm, int32_t *envs_per_thread);
+/* Violation counters of the CHECKED build (`make -C gym_os2r_b200/csrc libos2r_checked.so`: the step kernel validates
+ * its lane-sort permutation, env indices, terminal-record capacity and a shared-memory guard word; violations are
+ * counted, not trapped). out8[0..4] = counts (see os2r_kernels.cu), out8[7] = 1 when the loaded library was built
+ * with the checks (0: the counters are always zero). */
+int32_t os2r_debug_counters(int32_t device, uint64_t *out8, int32_t clear);
 /* fp32 FMA-pipe peak microbenchmark on the handle's device: returns TFLOP/s (2 flop per FMA)
  * measured with CUDA events (MEASURED_PEAKS.json has no fp32 entry). */
 int32_t os2r_measure_fp32_peak(int32_t device, double *tflops_out, double *sm_clock_mhz_out);

@@ -253,7 +253,7 @@ def test_golden_task_kat_through_kernel(golden):
     for (mode, variant, reward), cases in by_cfg.items():
         task, cm, cfg = make_config(mode, variant, reward, substeps=0)
         N, n = len(cases), cm.n_dof
-        W = 2 * n + (n + 9) + 2
+        W = 2 * n + (n + 3 * cm.struct.n_contacts) + 2
         st = np.zeros((N, W))
         for i, k in enumerate(cases):
             st[i, :n], st[i, n:2 * n] = chain_state(task, cm, k['q'], k['v'])
@@ -772,6 +772,87 @@ def test_contact_rollout_statistics_match_oracle():
     assert landed.mean() > 0.9, landed.mean()
     assert np.abs(td_g - td_o)[landed].max() <= 2, (td_g[landed], td_o[landed])
     assert abs(ret_g.mean() - ret_o.mean()) <= 0.02 * max(1.0, abs(ret_o.mean()))
+    eng.close()
+
+
+def test_hip_bracket_proxy_of_the_free_hip_model():
+    """the free-hip model carries a fourth contact proxy on the hip bracket (hip_link), which the
+    free boom_connector joint can swing into the ground (tests/test_host_logic.py holds the geometric argument). With
+    the bracket turned down and the boom low the proxy presses on the ground: normal impulse on proxy 0, device == oracle
+    (fp64 1e-10 after a step; fp32 within the contact bounds), and the env keeps stepping through the 4-proxy kernels."""
+    N = 256
+    task, cm, cfg = make_config('free_hip', reward='HoppingV1', pgs_tol=0.0)
+    assert cm.contact_names == ['hip_link', 'hip', 'knee', 'foot'] and cm.struct.n_contacts == 4
+    n, nc = cm.n_dof, 4
+    rng = np.random.RandomState(8)
+    from gym_os2r_b200.models import compiler
+    st = np.zeros((N, 2 * n + (n + 3 * nc) + 2))
+    ip, ib = cm.dof_of('planarizer_pitch_joint'), cm.dof_of('boom_connector_joint')
+    # boom_connector angle that points the bracket corner straight down (scan once at pitch 0), then per env a small
+    # offset from it and the boom pitch that puts the proxy 0 - 3 mm into the ground
+    scan = np.linspace(-np.pi, np.pi, 721)
+    zs = []
+    for bc in scan:
+        q = np.zeros(n); q[ib] = bc
+        zs.append(compiler.forward_kinematics(cm.struct, q)[2][0][2])
+    bc_down = scan[int(np.argmin(zs))]
+    for e in range(N):
+        q = np.zeros(n)
+        q[ib] = bc_down + rng.uniform(-0.4, 0.4)
+        q[cm.dof_of('hip_joint')], q[cm.dof_of('knee_joint')] = rng.uniform(-0.3, 0.3, 2)
+        z0 = compiler.forward_kinematics(cm.struct, q)[2][0][2] - cm.struct.contact_radius[0]     # proxy bottom at pitch 0
+        q[ip] = np.arcsin((-rng.uniform(0.0, 0.003) - z0) / 2.01)       # boom end height moves by ~2.01 sin(pitch)
+        st[e, :n] = q
+    st[:, n:2 * n] = rng.normal(0, 0.3, (N, n))
+    a = rng.uniform(-1, 1, (N, 2)).astype(np.float32)
+    for prec, tq, tv in ((64, 1e-10, 1e-8), (32, 5e-7, 5e-4)):
+        eng = Engine(cm, cfg, N, seed=1, precision=prec)
+        orc = oracle.Oracle(cm.struct, cfg, N, seed=1, nthreads=8)
+        eng.set_state(st)
+        orc.state[:] = eng.get_state()
+        eng.step(torch.as_tensor(a, device='cuda'))
+        orc.step(a.astype(np.float64))
+        sg = eng.get_state()
+        pressed = orc.state[:, 3 * n] > 0                       # normal impulse of proxy 0 = hip_link
+        assert pressed.mean() > 0.1, pressed.mean()     # still pressing after the 10 iterations (the others bounced or turned away)
+        assert np.array_equal(sg[:, 3 * n] > 0, pressed) or prec == 32
+        eq = np.abs(sg[:, :n] - orc.state[:, :n]).max(1)
+        ev = np.abs(sg[:, n:2 * n] - orc.state[:, n:2 * n]).max(1)
+        if prec == 64:
+            assert eq.max() < tq and ev.max() < tv, (eq.max(), ev.max())
+        else:
+            assert np.median(eq) < tq and np.median(ev) < tv and np.quantile(eq, 0.95) < 20 * tq, (np.median(eq), np.median(ev))
+        eng.close()
+
+
+@pytest.mark.parametrize('mode', ['fixed_hip', 'free_hip'])
+def test_lay_reset_rollout_statistics_match_oracle(mode):
+    """Documented contact tolerance restated for the `lay` resets (every link starts 2 - 3 cm above the ground and drops
+    onto it): first touchdown within +-2 env steps for >= 99 % of the envs (cap 6), 150-step return within 2 %."""
+    N, T = 512, 150
+    task, cm, cfg = make_config(mode, reward='BalancingV1', reset_positions=('lay',), reset_randomized=True, pgs_tol=1e-6)
+    eng = Engine(cm, cfg, N, seed=33)
+    orc = oracle.Oracle(cm.struct, cfg, N, seed=33, nthreads=16)
+    n, nc = cm.n_dof, cm.struct.n_contacts
+    eng.reset(); orc.reset()
+    orc.state[:] = eng.get_state()
+    rng = np.random.RandomState(4)
+    td_g = np.full(N, -1); td_o = np.full(N, -1)
+    ret_g = np.zeros(N); ret_o = np.zeros(N)
+    for t in range(T):
+        a = (0.3 * rng.uniform(-1, 1, (N, 2))).astype(np.float32)
+        _, r_g, _, _ = eng.step(torch.as_tensor(a, device='cuda'))
+        _, r_o, _, _, _ = orc.step(a.astype(np.float64))
+        ret_g += r_g.cpu().numpy(); ret_o += r_o
+        lam_g = eng.get_state()[:, 3 * n:3 * n + 3 * nc:3]
+        td_g = np.where((td_g < 0) & (lam_g > 0).any(1), t, td_g)
+        td_o = np.where((td_o < 0) & (orc.state[:, 3 * n:3 * n + 3 * nc:3] > 0).any(1), t, td_o)
+    landed = (td_o >= 0) & (td_g >= 0)
+    assert landed.mean() > 0.98, landed.mean()
+    d = np.abs(td_g - td_o)[landed]
+    print(f'lay touchdown step difference histogram ({mode}):', np.bincount(d, minlength=3).tolist())
+    assert (d <= 2).mean() >= 0.99 and d.max() <= 6, np.bincount(d).tolist()
+    assert abs(ret_g.mean() - ret_o.mean()) <= 0.02 * max(1.0, abs(ret_o.mean())), (ret_g.mean(), ret_o.mean())
     eng.close()
 
 

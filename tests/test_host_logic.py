@@ -65,6 +65,46 @@ def test_forward_kinematics_facts():
     assert abs(Rs[2][0, 0]) == pytest.approx(7.96e-4, rel=0.02)
 
 
+def test_contact_proxy_set_covers_the_links_that_can_reach_the_ground():
+    """the reference collides every link's mesh (monopod.urdf:39-45,85-90,128-133,185-195,
+    248-256). Which links can touch the ground plane at all is a geometric fact checked here from the mesh extents:
+      * boom tube (r 0.0127 about the boom axis, y in [-2, 0]) and, where boom_connector is fixed, the hip bracket
+        (bbox corner farthest from the boom axis: local (0.01, -0.015, 0.085)) are shielded by the hip sphere (r 0.02
+        about the hip joint, 0.035 m outboard of the bracket): whatever the leg does, the sphere's lowest point is
+        lower -> no proxy needed, none shipped;
+      * with boom_connector FREE (`monopod`, task mode free_hip) the bracket turns about its own x axis and its far corner
+        (0.107 m from that axis) swings far below the hip sphere -> the model carries a fourth proxy `hip_link`;
+      * the central pivot's bottom face lies exactly in the ground plane and never translates: a zero-depth contact that
+        carries no load (the pivot hangs from the world joint) -> ignored."""
+    import itertools
+    full, fh = _compile('monopod'), _compile('monopod-fixed_hip')
+    assert full.contact_names == ['hip_link', 'hip', 'knee', 'foot'] and full.struct.n_contacts == 4
+    assert list(full.struct.contact_body[:4]) == [2, 3, 3, 4]
+    assert fh.contact_names == ['hip', 'knee', 'foot']
+    # hip bracket bbox corners and boom tip in the frame of the body that carries them in the fixed_hip model (boom)
+    m = full.struct
+    R_bc = np.array(m.tree_R[2][:]).reshape(3, 3)
+    p_bc = np.array(m.tree_p[2][:])
+    corners = [p_bc + R_bc @ np.array(c) for c in itertools.product((-0.01, 0.01), (-0.015, 0.065), (-0.015, 0.085))]
+    tip = np.array([0.0, -2.0, 0.0])
+    rng = np.random.RandomState(0)
+    for _ in range(300):
+        # boom pitched low enough for anything at its end to come within 5 cm of the ground
+        q = np.array([rng.uniform(-3, 3), rng.uniform(-0.07, -0.02), rng.uniform(-3.2, 3.2), rng.uniform(-3.2, 3.2)])
+        Rs, ps, cs = compiler.forward_kinematics(fh.struct, q)
+        hip_bottom = cs[0][2] - fh.struct.contact_radius[0]
+        lowest_bracket = min((ps[1] + Rs[1] @ c)[2] for c in corners)
+        boom_tip_bottom = (ps[1] + Rs[1] @ tip)[2] - 0.0127
+        assert lowest_bracket - hip_bottom > 0.004 and boom_tip_bottom - hip_bottom > 0.006, (q, lowest_bracket, boom_tip_bottom, hip_bottom)
+    # free boom_connector: turned by about +-2 rad the bracket corner is the lowest point of the whole robot
+    worst = 0.0
+    for bc in np.linspace(-3.1, 3.1, 63):
+        q = np.array([0.0, 0.0, bc, 0.5, -1.0])
+        Rs, ps, cs = compiler.forward_kinematics(m, q)
+        worst = max(worst, (cs[1][2] - m.contact_radius[1]) - (cs[0][2] - m.contact_radius[0]))
+    assert worst > 0.06          # the bracket proxy reaches > 6 cm below the hip sphere
+
+
 def test_unsupported_urdf_features_raise(tmp_path):
     text = open(gym_os2r_b200.models.assets.get_model_file('monopod')).read()
     bad = tmp_path / 'bad.urdf'
