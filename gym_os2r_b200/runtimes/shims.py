@@ -72,6 +72,19 @@ class ModelShim:
     def joint_generalized_force_targets(self, names):
         return [self._targets.get(n, 0.0) for n in names]
 
+    def links_in_contact(self):
+        """ScenarIO ``Model.links_in_contact()``: names of the links whose collision proxies carry a normal impulse."""
+        cm = self._rt._compiled
+        n, nc = cm.n_dof, cm.struct.n_contacts
+        st = self._rt.engine.get_state()[self._e]
+        link_of = {'hip': 'upper_leg_link', 'knee': 'upper_leg_link', 'foot': 'lower_leg_link', 'hip_link': 'hip_link'}
+        out = []
+        for c in range(nc):
+            link = link_of.get(cm.contact_names[c], cm.contact_names[c])
+            if st[3 * n + 3 * c] > 0 and link not in out:
+                out.append(link)
+        return out
+
     def set_joint_control_mode(self, _mode, _names=None):
         return True
 

@@ -962,3 +962,20 @@ def test_dart_golden_trajectories_if_present():
             worst_v = max(worst_v, np.abs(s[:, [cm.n_dof + d for d in order]] - qd_ref[t]).max())
         eng.close()
         assert worst_q <= 1e-4 and worst_v <= 1e-3, (f, worst_q, worst_v)
+
+
+def test_dart_recorder_selftest_round_trip(tmp_path):
+    """tools/record_dart_golden.py --selftest: the recording loop (single env through the gym API, exactly what runs
+    against gym-ignition on a machine that has it), the file format and the tolerance report (tools/dart_report.py)
+    exercised end to end against this repo's own runtime; a recording of this runtime must be reproduced exactly."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = str(tmp_path / 'selftest.npz')
+    res = subprocess.run([sys.executable, os.path.join(root, 'tools', 'record_dart_golden.py'), '--selftest', '--out', out,
+                          '--steps', '130', '--envs', '2'], capture_output=True, text=True, cwd=root)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+    assert 'selftest ok' in res.stdout and "touchdown step difference histogram over 2 envs" in res.stdout
+    g = np.load(out, allow_pickle=True)
+    assert g['q'].shape == (130, 2, 4) and g['in_contact'].any() and str(g['task_mode']) == 'fixed_hip'
