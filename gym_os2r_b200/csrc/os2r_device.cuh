@@ -351,7 +351,9 @@ struct ColdSlots {
     static constexpr int CX = VLO + N;            // [3*NC] contact centres (world)
     static constexpr int ACT = CX + 3 * NC;       // [2] this step's clamped action (0 when it was not finite)
     static constexpr int AFIN = ACT + 2;          // [1] 1 = the action was finite
-    static constexpr int QHI = AFIN + 1;          // [N] q_hi, v parked after the last iteration: the fp64 epilogue runs
+    static constexpr int AOLD = AFIN + 1;         // [2] previous action (loaded in the prologue, used by the epilogue)
+    static constexpr int MISC = AOLD + 2;         // [3] episode step counter, episode return (lo, hi words), bit patterns
+    static constexpr int QHI = MISC + 3;          // [N] q_hi, v parked after the last iteration: the fp64 epilogue runs
     static constexpr int VHI = QHI + N;           // [N]   once per env and reads everything per half from here
     static constexpr int COUNT = VHI + N;
 };

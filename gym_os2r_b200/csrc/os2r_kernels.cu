@@ -267,6 +267,12 @@ step_kernel(const __grid_constant__ ModelDev<typename VT<V>::S> M, const __grid_
 #pragma unroll
     for (int c = 0; c < NC; ++c) ld_mu[c] = gather<V>(S.mu + c * NE, e);
     E.gz = gather<V>(S.gravity_z, e);
+    // episode bookkeeping and the previous action are only needed by the epilogue, but their loads are issued here with
+    // all the others (one DRAM round trip for the lot) and the values parked in shared memory as bit patterns
+    static_assert(LANES == 1, "the bookkeeping slots hold one env per thread");
+    const T a_old0 = __ldcg(S.a_prev + e[0]), a_old1 = __ldcg(S.a_prev + NE + e[0]);
+    const int steps_ld = __ldcg(S.steps + e[0]);
+    const double ret_ld = __ldcg(S.ret + e[0]);
     float ax_[LANES], ay_[LANES], afin_[LANES];
 #pragma unroll
     for (int h = 0; h < LANES; ++h) {
@@ -304,6 +310,11 @@ step_kernel(const __grid_constant__ ModelDev<typename VT<V>::S> M, const __grid_
     C(SL::ACT) = act_x;
     C(SL::ACT + 1) = act_y;
     C(SL::AFIN) = from_halves<V>(afin_);
+    C(SL::AOLD) = a_old0;
+    C(SL::AOLD + 1) = a_old1;
+    C(SL::MISC) = int_as_real(T(0), steps_ld);
+    C(SL::MISC + 1) = int_as_real(T(0), __double2loint(ret_ld));
+    C(SL::MISC + 2) = int_as_real(T(0), __double2hiint(ret_ld));
 #ifdef OS2R_CHECKED
     C(SL::COUNT) = V(12345.0f);          // guard word behind the last slot (the checked build allocates one more slot)
 #endif
@@ -327,10 +338,10 @@ step_kernel(const __grid_constant__ ModelDev<typename VT<V>::S> M, const __grid_
         const bool ok = LANES == 1 ? valid[0] : (h ? valid[LANES - 1] : valid[0]);
         if (!ok) continue;
         const int64_t en = LANES == 1 ? e[0] : (h ? e[LANES - 1] : e[0]);
-        const int steps_in = __ldcg(S.steps + en);
+        const int steps_in = real_as_int(C.half(SL::MISC, h));
         int reset_idx = __ldcg(S.reset_id + en);
-        const double ret_in = __ldcg(S.ret + en);
-        const double a_old[2] = {(double)__ldcg(S.a_prev + en), (double)__ldcg(S.a_prev + NE + en)};
+        const double ret_in = __hiloint2double(real_as_int(C.half(SL::MISC + 2, h)), real_as_int(C.half(SL::MISC + 1, h)));
+        const double a_old[2] = {(double)C.half(SL::AOLD, h), (double)C.half(SL::AOLD + 1, h)};
         const float actx = (float)C.half(SL::ACT, h), acty = (float)C.half(SL::ACT + 1, h);
         double q[N], v[N];
         bool finite = C.half(SL::AFIN, h) != T(0);
