@@ -96,4 +96,4 @@ if __name__ == '__main__':
             for N in (32, 1024, 9472, 16384, 32768):
                 P(steady(N=N, steps=300)); P(fresh(N=N))
         if which == 'modes':
-            P(steady(mode='fixed', pre=1000)); P(steady(mode='simple', pre=100))
+            P(steady(mode='fixed', pre=1000)); P(fresh(mode='fixed')); P(steady(mode='simple', pre=100))

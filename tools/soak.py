@@ -1,5 +1,6 @@
 import sys, time
-sys.path.insert(0, '/root/repo')
+import os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 from gym_os2r_b200 import randomizers
 from gym_os2r_b200.common import make_mp_envs
@@ -21,5 +22,5 @@ for env_id, mode in (('Monopod-balance-v1', 'fixed_hip'), ('Monopod-hop-v1', 'fr
                   'mean len', st['sum_length'] / max(st['episodes'], 1), 'obs finite', bool(torch.isfinite(obs).all()), 'max|obs|', float(obs.abs().max()), flush=True)
     s = eng.get_state()
     n = eng.model.n_dof
-    print(mode, 'state finite', np.isfinite(s).all(), 'max|q|', np.abs(s[:, :n]).max(), 'max|qd|', np.abs(s[:, n:2*n]).max(), 'contact frac', (s[:, 3*n:3*n+9:3] > 0).mean(0).round(3))
+    print(mode, 'state finite', np.isfinite(s).all(), 'max|q|', np.abs(s[:, :n]).max(), 'max|qd|', np.abs(s[:, n:2*n]).max(), 'contact frac', (s[:, 3*n:3*n+3*eng.model.n_contacts:3] > 0).mean(0).round(3))
     envs.close()
