@@ -259,3 +259,28 @@ def test_shard_range_and_lazy_infos():
         assert 'TimeLimit.truncated' not in infos[1] and infos[2]['terminal_observation'].tolist() == [4.0, 5.0]
         assert [i['reset_orientation'] for i in infos] == ['stand', 'lay', 'lay']
         assert sorted(infos.terminal_indices.tolist()) == [1, 2]
+
+
+def test_numa_binding_helper_never_fails_and_never_widens_the_mask():
+    """bind_to_gpu_numa_node: without NVML / a GPU it reports why and leaves the affinity alone."""
+    import os
+    from gym_os2r_b200.common.distributed import bind_to_gpu_numa_node
+    before = os.sched_getaffinity(0)
+    out = bind_to_gpu_numa_node(0)
+    assert isinstance(out, dict) and 'bound' in out
+    assert os.sched_getaffinity(0) <= before
+    os.sched_setaffinity(0, before)
+
+
+def test_randomizer_wrapper_forwards_num_physics_rollouts():
+    """MonopodEnvRandomizer(num_physics_rollouts=K) -> os2r_task_cfg.gravity_redraw_resets (randomizers/monopod.py:36,371)."""
+    import functools
+    from gym_os2r_b200 import randomizers
+    from gym_os2r_b200.common import make_env_from_id
+    env = randomizers.monopod.MonopodEnvRandomizer(env=functools.partial(make_env_from_id, env_id='Monopod-balance-v1'),
+                                                   num_physics_rollouts=4)
+    cfg = env.unwrapped._cfg
+    assert cfg.gravity_redraw_resets == 4 and cfg.randomize_gravity == 1 and cfg.reset_randomized == 1
+    with pytest.raises(ValueError):
+        randomizers.monopod.MonopodEnvRandomizer(env=functools.partial(make_env_from_id, env_id='Monopod-balance-v1'),
+                                                 num_physics_rollouts=-1)
