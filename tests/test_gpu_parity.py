@@ -974,8 +974,8 @@ def test_dart_recorder_selftest_round_trip(tmp_path):
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     out = str(tmp_path / 'selftest.npz')
     res = subprocess.run([sys.executable, os.path.join(root, 'tools', 'record_dart_golden.py'), '--selftest', '--out', out,
-                          '--steps', '130', '--envs', '2'], capture_output=True, text=True, cwd=root)
+                          '--steps', '220', '--envs', '2'], capture_output=True, text=True, cwd=root)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
-    assert 'selftest ok' in res.stdout and "touchdown step difference histogram over 2 envs" in res.stdout
+    assert 'selftest ok' in res.stdout and 'touchdown step difference histogram over' in res.stdout
     g = np.load(out, allow_pickle=True)
-    assert g['q'].shape == (130, 2, 4) and g['in_contact'].any() and str(g['task_mode']) == 'fixed_hip'
+    assert g['q'].shape == (220, 2, 4) and g['in_contact'].any() and str(g['task_mode']) == 'fixed_hip'
