@@ -13,14 +13,31 @@ import numpy as np
 
 
 class _JointShim:
-    def __init__(self, name):
-        self._name = name
+    """ScenarIO ``Joint`` of one env: position / velocity access and reset (examples/ignition_interaction.py)."""
+
+    def __init__(self, name, model=None):
+        self._name, self._model = name, model
 
     def name(self):
         return self._name
 
+    def to_gazebo(self):
+        return self
+
     def set_joint_max_generalized_force(self, _values):
         return True   # the torque limit is the constant max_torque of the compiled model
+
+    def joint_position(self):
+        return self._model.joint_positions([self._name])
+
+    def joint_velocity(self):
+        return self._model.joint_velocities([self._name])
+
+    def reset_position(self, value):
+        return self._model.reset_joint_positions([float(value)], [self._name])
+
+    def reset_velocity(self, value):
+        return self._model.reset_joint_velocities([float(value)], [self._name])
 
 
 class ModelShim:
@@ -89,7 +106,9 @@ class ModelShim:
         return True
 
     def get_joint(self, name):
-        return _JointShim(name)
+        if name not in self._rt._compiled.joint_names:
+            raise KeyError(f'the model has no moving joint {name!r} (joints: {self._rt._compiled.joint_names})')
+        return _JointShim(name, self)
 
 
 class WorldShim:

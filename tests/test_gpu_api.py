@@ -202,3 +202,32 @@ def test_policy_rollout_stays_on_device_and_checkpoints():
     assert len(model.joint_positions(['hip_joint', 'knee_joint'])) == 2
     assert rt.world.to_gazebo().set_gravity((0, 0, -5.0)) and rt.world.gravity()[2] == -5.0
     envs.close()
+
+
+def test_joint_level_shims_and_single_iteration_runtime():
+    """examples/ignition_interaction.py: per-joint reset / read-back through the ScenarIO-style shims, and a runtime whose
+    env step is ONE physics iteration (agent_rate == physics_rate): ten such steps with a held action equal one ordinary
+    env step (the reference's zero-order-hold loop, runtimes/gazebo_runtime.py:65-97)."""
+    mk = lambda **kw: randomizers.monopod_no_rand.MonopodEnvNoRandomizer(env=functools.partial(
+        make_env_from_id, env_id='Monopod-balance-v1', task_mode='fixed_hip', **kw))
+    fine, coarse = mk(agent_rate=10000, physics_rate=10000), mk()
+    assert fine.unwrapped.num_of_steps_per_run == 1 and coarse.unwrapped.num_of_steps_per_run == 10
+    for env in (fine, coarse):
+        env.reset()
+        m = env.unwrapped.task.model
+        assert m.get_joint('planarizer_pitch_joint').to_gazebo().reset_position(0.3)
+        assert m.get_joint('hip_joint').to_gazebo().reset_position(-0.4)
+        assert m.get_joint('hip_joint').joint_position()[0] == pytest.approx(-0.4, abs=1e-7)
+    with pytest.raises(KeyError):
+        fine.unwrapped.task.model.get_joint('boom_connector_joint')      # fixed in this model
+    a = [0.3, -0.2]
+    for _ in range(10):
+        fine.step(a)
+    coarse.step(a)
+    names = ['planarizer_pitch_joint', 'hip_joint', 'knee_joint', 'planarizer_yaw_joint']
+    qf, qc = fine.unwrapped.task.model.joint_positions(names), coarse.unwrapped.task.model.joint_positions(names)
+    vf, vc = fine.unwrapped.task.model.joint_velocities(names), coarse.unwrapped.task.model.joint_velocities(names)
+    np.testing.assert_array_equal(qf, qc)
+    np.testing.assert_array_equal(vf, vc)
+    assert fine.unwrapped.task.model.links_in_contact() == []
+    fine.close(); coarse.close()
