@@ -670,6 +670,7 @@ int32_t os2r_set_randomization(os2r_env *h, const os2r_task_cfg *cfg) {
     t.grav_mean = cfg->grav_mean; t.grav_std = cfg->grav_std;
     t.reset_randomized = cfg->reset_randomized; t.randomize_params = cfg->randomize_params;
     t.randomize_gravity = cfg->randomize_gravity; t.gravity_redraw_resets = cfg->gravity_redraw_resets;
+    t.simple_sample_reset = cfg->simple_sample_reset;   // derived from reset_randomized (`simple` mode + NoRandomizer)
     h->task = t;
     // a damping range on a model with damped joints keeps the implicit-damping build; nothing else depends on the ranges
     return 0;

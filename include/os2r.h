@@ -183,7 +183,8 @@ int32_t os2r_create_tuned(const os2r_model *model, const os2r_task_cfg *task, in
 int32_t os2r_destroy(os2r_env *env);
 
 /* Replace the randomisation ranges / switches of a live handle (mass_lo..grav_std, reset_randomized,
- * randomize_params, randomize_gravity, gravity_redraw_resets of `cfg`; everything else in `cfg` is ignored). Takes
+ * randomize_params, randomize_gravity, simple_sample_reset, gravity_redraw_resets of `cfg`; everything else in `cfg`
+ * is ignored). Takes
  * effect from the next reset of each env. Replaces editing MonopodRandomizersMixin's randomization_config
  * (randomizers/monopod.py:182-215). */
 int32_t os2r_set_randomization(os2r_env *env, const os2r_task_cfg *cfg);
