@@ -231,3 +231,29 @@ def test_joint_level_shims_and_single_iteration_runtime():
     np.testing.assert_array_equal(vf, vc)
     assert fine.unwrapped.task.model.links_in_contact() == []
     fine.close(); coarse.close()
+
+
+def test_handles_on_two_devices_in_one_process():
+    """One process may hold handles on several GPUs: the > 48 KB dynamic shared memory opt-in of the wide-block step kernel
+    is a per-device attribute and is made per handle (os2r_create under its device guard), so the SECOND device's launches
+    work too; results are independent of the device."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs two GPUs (run with gpurun --gpus 2)')
+    from gym_os2r_b200.runtimes.engine import Engine
+    from helpers import make_config
+    task, cm, cfg = make_config('free_hip', reward='HoppingV1', reset_randomized=True, randomize_params=True, pgs_tol=1e-6)
+    N = 148 * 224                                   # wide blocks: 5 DoF + 4 proxies need ~73 KB of shared memory per block
+    out = []
+    for dev in (0, 1):
+        eng = Engine(cm, cfg, N, device=dev, seed=3)
+        assert eng.kernel_info()['block_threads'] == 224
+        eng.reset()
+        g = torch.Generator(device=f'cuda:{dev}'); g.manual_seed(1)
+        with torch.cuda.device(dev):
+            for _ in range(3):
+                obs, rew, done, _ = eng.step(torch.rand((N, 2), device=f'cuda:{dev}', generator=g) * 2 - 1)
+            torch.cuda.synchronize(dev)
+        out.append((eng, obs.cpu().numpy().copy(), eng.get_state()))
+    assert np.array_equal(out[0][1], out[1][1]) and np.array_equal(out[0][2], out[1][2])
+    for eng, _, _ in out:
+        eng.close()
