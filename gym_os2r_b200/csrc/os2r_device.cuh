@@ -337,9 +337,20 @@ enum { DRAW_RESET = 0, DRAW_PITCH = 1, DRAW_NOISE = 2, DRAW_LAYSIDE = 4, DRAW_DI
 // the compensation terms of the (hi, lo) state pairs, torques and the contact-sphere centres.
 // Only what every phase needs (q_hi, v, gravity) stays in registers. A slot holds one V: a float / double, or in the
 // pair build the f2 of the thread's two envs (8-byte accesses, half h of slot k is the float at byte offset 4h).
+// Contact proxies whose constraint rows (G, 1/A, b) live in SHARED MEMORY between their set-up and the sweeps instead
+// of registers (bit c = proxy c). The sweep loop of the 5-DoF model with all four proxies in registers needs ~130 live
+// registers against the 128 two resident 7-warp blocks allow (640 B of spills, 9.5 % of the executed instructions were
+// local-memory traffic); the bracket and the foot press in < 3 % of the envs each, so their rows are parked.
+template <int N, int NC>
+__host__ __device__ constexpr unsigned parked_rows_mask() {
+    return (N == 5 && NC == 4) ? 0b1001u : (N == 5 && NC == 3) ? 0b100u : 0u;
+}
+__host__ __device__ constexpr int popcount_c(unsigned m) { return m ? (int)(m & 1u) + popcount_c(m >> 1) : 0; }
+
 template <int N, int NC>
 struct ColdSlots {
     static constexpr int ROWS = N + 3 * NC;
+    static constexpr unsigned PARKED = parked_rows_mask<N, NC>();
     static constexpr int LAM = 0;                 // [ROWS]
     static constexpr int MASS = LAM + ROWS;       // [N] mass coefficient
     static constexpr int DAMP = MASS + N;         // [N] damping
@@ -355,7 +366,12 @@ struct ColdSlots {
     static constexpr int MISC = AOLD + 2;         // [3] episode step counter, episode return (lo, hi words), bit patterns
     static constexpr int QHI = MISC + 3;          // [N] q_hi, v parked after the last iteration: the fp64 epilogue runs
     static constexpr int VHI = QHI + N;           // [N]   once per env and reads everything per half from here
-    static constexpr int COUNT = VHI + N;
+    static constexpr int GROW = VHI + N;          // [parked proxies][3 rows][N + 2]: G_r, reciprocal diagonal, row velocity
+    static constexpr int COUNT = GROW + popcount_c(PARKED) * 3 * (N + 2);
+    // slot of entry k (0..N-1: G, N: reciprocal diagonal, N+1: row velocity) of row d of parked proxy c
+    __host__ __device__ static constexpr int grow(int c, int d, int k) {
+        return GROW + (popcount_c(PARKED & ((1u << c) - 1u)) * 3 + d) * (N + 2) + k;
+    }
 };
 
 template <typename V, int STRIDE>
@@ -668,24 +684,35 @@ __device__ __forceinline__ void physics_iteration(const ModelDev<typename VT<V>:
 #pragma unroll
             for (int d = 0; d < 3; ++d) {
                 V a = V(0), b = (d == 0) ? -bounce : V(0);
+                V g[N];
 #pragma unroll
                 for (int k = 0; k < N; ++k) {
                     V s = J[d][k];
 #pragma unroll
-                    for (int m = 0; m < k; ++m) s -= L[k][m] * Gc[c][d][m];
-                    Gc[c][d][k] = s * Ld[k];
-                    a += Gc[c][d][k] * Gc[c][d][k];
-                    b += Gc[c][d][k] * z0[k];
+                    for (int m = 0; m < k; ++m) s -= L[k][m] * g[m];
+                    g[k] = s * Ld[k];
+                    a += g[k] * g[k];
+                    b += g[k] * z0[k];
                 }
                 // An env of the pair that is NOT in contact gets a dead row: relaxation factor, row velocity and
                 // impulse 0, so every update below computes lam' = 0, dlam = 0 for it (a single-env build never
                 // gets here for such an env: the selects are no-ops).
-                Ac[c][d] = sel_t(on_c, rcp_t(a * M.cfm1_contact), V(0));
-                bc[c][d] = sel_t(on_c, b, V(0));
+                const V ra = sel_t(on_c, rcp_t(a * M.cfm1_contact), V(0)), rb = sel_t(on_c, b, V(0));
                 const V l = sel_t(on_c, C(SL::LAM + N + 3 * c + d), V(0));   // warm start
 #pragma unroll
-                for (int k = 0; k < N; ++k) z[k] += Gc[c][d][k] * l;
+                for (int k = 0; k < N; ++k) z[k] += g[k] * l;
                 C(SL::LAM + N + 3 * c + d) = l;
+                if ((SL::PARKED >> c) & 1u) {          // compile-time after unrolling: rows of a rarely pressed proxy
+#pragma unroll
+                    for (int k = 0; k < N; ++k) C(SL::grow(c, d, k)) = g[k];
+                    C(SL::grow(c, d, N)) = ra;
+                    C(SL::grow(c, d, N + 1)) = rb;
+                } else {
+#pragma unroll
+                    for (int k = 0; k < N; ++k) Gc[c][d][k] = g[k];
+                    Ac[c][d] = ra;
+                    bc[c][d] = rb;
+                }
             }
         } else {
 #pragma unroll
@@ -733,10 +760,21 @@ __device__ __forceinline__ void physics_iteration(const ModelDev<typename VT<V>:
                 for (int d = 0; d < 3; ++d) {
                     const int r = N + 3 * c + d;
                     const V lam = (d == 0) ? ln : C(SL::LAM + r);
-                    V w = bc[c][d];
+                    V g[N], ra, w;
+                    if ((SL::PARKED >> c) & 1u) {      // compile-time after unrolling
 #pragma unroll
-                    for (int k = 0; k < N; ++k) w += Gc[c][d][k] * z[k];
-                    V nl = lam * kc1 - w * Ac[c][d];
+                        for (int k = 0; k < N; ++k) g[k] = C(SL::grow(c, d, k));
+                        ra = C(SL::grow(c, d, N));
+                        w = C(SL::grow(c, d, N + 1));
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < N; ++k) g[k] = Gc[c][d][k];
+                        ra = Ac[c][d];
+                        w = bc[c][d];
+                    }
+#pragma unroll
+                    for (int k = 0; k < N; ++k) w += g[k] * z[k];
+                    V nl = lam * kc1 - w * ra;
                     if (d == 0) nl = fmax_t(nl, V(0));
                     else {
                         const V lim = C(SL::MU + c) * ln;
@@ -746,7 +784,7 @@ __device__ __forceinline__ void physics_iteration(const ModelDev<typename VT<V>:
                     if (d == 0) ln = nl;
                     const V dl = nl - lam;
 #pragma unroll
-                    for (int k = 0; k < N; ++k) z[k] += Gc[c][d][k] * dl;
+                    for (int k = 0; k < N; ++k) z[k] += g[k] * dl;
                     C(SL::LAM + r) = nl;
                 }
             }
