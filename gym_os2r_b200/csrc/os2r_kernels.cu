@@ -472,11 +472,13 @@ static constexpr size_t step_smem_bytes() {
     return cold > sort ? cold : sort;
 }
 
-// Threads per block of the step kernel for a batch. Wide blocks (7 warps) give the lane sort enough envs to fill whole
-// warps with one contact class; they need about one block per SM to pay off.
-// Small batches and the fp64 verification build keep 2-warp blocks (more SMs busy).
+// Threads per block of the step kernel for a batch. Wide blocks (7 warps, two per SM at 128 registers) give the lane
+// sort enough envs to fill whole warps with one contact class. Batches that fit ONE wave of the narrow build (four 2-warp
+// blocks per SM at up to 255 registers: 37 888 envs on 148 SMs) run it instead — more registers, more instruction-level
+// parallelism, and no SM that holds two wide blocks while its neighbour holds one (measured, fixed_hip steady state:
+// 36 864 envs 67.0 us narrow / 84.3 wide; 40 960 envs 104.7 narrow (two waves) / 85.5 wide). fp64: narrow blocks only.
 int step_block_threads(int build, int64_t n_envs, int sm_count) {
-    if (build == OS2R_BUILD_F32 && n_envs >= (int64_t)sm_count * OS2R_BLOCK_WIDE) return OS2R_BLOCK_WIDE;
+    if (build == OS2R_BUILD_F32 && n_envs > (int64_t)sm_count * 4 * OS2R_BLOCK) return OS2R_BLOCK_WIDE;
     return OS2R_BLOCK;
 }
 

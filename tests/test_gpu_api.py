@@ -242,7 +242,7 @@ def test_handles_on_two_devices_in_one_process():
     from gym_os2r_b200.runtimes.engine import Engine
     from helpers import make_config
     task, cm, cfg = make_config('free_hip', reward='HoppingV1', reset_randomized=True, randomize_params=True, pgs_tol=1e-6)
-    N = 148 * 224                                   # wide blocks: 5 DoF + 4 proxies need ~73 KB of shared memory per block
+    N = 148 * 4 * 64 + 224                          # wide blocks: 5 DoF + 4 proxies need ~110 KB of shared memory per block
     out = []
     for dev in (0, 1):
         eng = Engine(cm, cfg, N, device=dev, seed=3)
