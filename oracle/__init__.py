@@ -1,7 +1,8 @@
 """ctypes binding of the CPU oracle (oracle/os2r_oracle.c).
 
 TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's
-cpu_baseline / --impl reference legs. The product package never imports this module.
+cpu_baseline / --impl reference legs (and by the diagnostic scripts under tools/ that are themselves test infrastructure:
+parity report, regression-fixture generator, probes). The product package never imports this module.
 Physics parity is UNPINNED (no runnable DART here, no golden trajectories in the reference);
 task-logic parity is pinned by tests/golden/task_kat.json. See the header of os2r_oracle.c.
 """
