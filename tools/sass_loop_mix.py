@@ -1,6 +1,8 @@
 #!/usr/bin/env python
-"""Static instruction mix of the physics loop of one step_kernel instantiation (between the loop-top barrier and the
-backward branch): python tools/sass_loop_mix.py [N] [BLOCK] [MINB] [lib]"""
+"""Static instruction mix of the largest backward-branch region of one step_kernel instantiation (the physics loop plus
+whatever ptxas laid out inside its address range: unlikely blocks, the rolled epilogue) — for A/B comparisons of two builds
+(FP instructions against MOVs etc.), not a footprint measurement; the executed footprint comes from the ncu report
+(tools/ncu_by_source.py): python tools/sass_loop_mix.py [N] [BLOCK] [MINB] [lib]"""
 import os
 import re
 import subprocess
