@@ -13,7 +13,7 @@ MAX_OBS = 12
 MAX_RESETS = 8
 MAX_ROWS = MAX_DOF + 3 * MAX_CONTACTS
 N_ROLES = 5
-ABI_VERSION = 8
+ABI_VERSION = 9
 
 ROLE_HIP, ROLE_KNEE, ROLE_PITCH, ROLE_YAW, ROLE_BOOM_CONNECTOR = range(5)
 ROLE_OF_JOINT = {
@@ -73,7 +73,7 @@ class TaskCfg(C.Structure):
 
 class Tuning(C.Structure):
     """struct os2r_tuning (zero = defaults)"""
-    _fields_ = [('sort_margin', _f64), ('force_block', _i32), ('_reserved0', _i32), ('disable_root_fold', _i32),
+    _fields_ = [('sort_margin', _f64), ('force_block', _i32), ('disable_specialisation', _i32), ('disable_root_fold', _i32),
                 ('_pad', _i32)]
 
 
@@ -139,6 +139,7 @@ SYMBOLS = {
     'os2r_kernel_launches': (C.c_int64, [_vp]),
     'os2r_kernel_info': (_i32, [_vp, C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32),
                                 C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32)]),
+    'os2r_model_signature': (_i32, [C.POINTER(Model), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(_i32)]),
     'os2r_debug_counters': (_i32, [_i32, C.POINTER(C.c_uint64), _i32]),
     'os2r_measure_fp32_peak': (_i32, [_i32, C.POINTER(_f64), C.POINTER(_f64)]),
 }

@@ -128,6 +128,39 @@ void build_model_dev(const os2r_model &m, const os2r_tuning &tune, ModelDev<T> &
     for (int i = 0; i < m.n_dof; ++i) if (m.damping[i] != 0.0) d.any_damping = 1;
 }
 
+// Structure signature of a model (os2r_device.cuh): which joints' tree_R is the identity / a turn about the joint axis /
+// a turn about z in the normalised frames, and which components of tree_p / contact_pos are zero. |x| <= 1e-15 counts as
+// zero (the URDFs' literal rpy "1.57" leaves products of the order 1e-19 in entries that are structurally 0: they are
+// below half an ulp of the fp64 sum they would enter).
+void model_signature(const os2r_model &m, uint32_t *sj, uint32_t *sc) {
+    os2r_tuning tune;
+    memset(&tune, 0, sizeof(tune));
+    ModelDev<double> d;
+    build_model_dev<double>(m, tune, d);
+    auto z = [](double x) { return fabs(x) <= 1e-15; };
+    auto one = [](double x) { return fabs(x - 1.0) <= 1e-15; };
+    uint32_t J = 0, C = 0;
+    for (int i = m.n_dof - 1; i >= 0; --i) {
+        const double *R = d.tree_R[i], *p = d.tree_p[i];
+        uint32_t kind = OS2R_TREE_GENERAL;
+        if (i > 0) {   // joint 0 hangs off the world: its constant frame is used as it is
+            if (one(R[0]) && z(R[1]) && z(R[2]) && z(R[3]) && one(R[4]) && z(R[5]) && z(R[6]) && z(R[7]) && one(R[8])) kind = OS2R_TREE_IDENTITY;
+            else if (one(R[0]) && z(R[1]) && z(R[2]) && z(R[3]) && z(R[6]) && z(R[4] - R[8]) && z(R[5] + R[7])) kind = OS2R_TREE_XTURN;
+            else if (one(R[8]) && z(R[2]) && z(R[5]) && z(R[6]) && z(R[7])) kind = OS2R_TREE_ZTURN;
+            else if (one(R[4]) && z(R[1]) && z(R[3]) && z(R[5]) && z(R[7])) kind = OS2R_TREE_YTURN;
+        }
+        uint32_t pm = 0;
+        for (int c = 0; c < 3; ++c) if (i == 0 || !z(p[c])) pm |= 1u << c;
+        J = (J << 6) | (pm << 3) | kind;
+    }
+    for (int c = m.n_contacts - 1; c >= 0; --c) {
+        uint32_t cm = 0;
+        for (int k = 0; k < 3; ++k) if (!z(d.contact_pos[c][k])) cm |= 1u << k;
+        C = (C << 3) | cm;
+    }
+    *sj = J; *sc = C;
+}
+
 }  // namespace
 
 struct os2r_env {
@@ -142,6 +175,7 @@ struct os2r_env {
     int64_t first_env_id = 0;
     uint64_t seed = 0;
     int rows = 0;
+    uint32_t sig_j = 0, sig_c = 0;   // structure signature the step kernel is picked by
     // device memory
     void *real_block = nullptr;      // all T-typed SoA arrays, one allocation
     size_t real_count = 0;           // elements of T
@@ -312,9 +346,9 @@ int set_params_impl(os2r_env *h, StateDev<T> &S, const double *in) {
 int do_step(os2r_env *h, const StepIO &io, cudaStream_t stream) {
     cudaError_t e;
     if (h->precision == 32)
-        e = launch_step<float>(h->build, h->model.n_dof, h->model.n_contacts, h->block, h->m32, h->taskdev, h->s32, io, h->stats, stream);
+        e = launch_step<float>(h->build, h->model.n_dof, h->model.n_contacts, h->block, h->sig_j, h->sig_c, h->m32, h->taskdev, h->s32, io, h->stats, stream);
     else
-        e = launch_step<double>(h->build, h->model.n_dof, h->model.n_contacts, h->block, h->m64, h->taskdev, h->s64, io, h->stats, stream);
+        e = launch_step<double>(h->build, h->model.n_dof, h->model.n_contacts, h->block, h->sig_j, h->sig_c, h->m64, h->taskdev, h->s64, io, h->stats, stream);
     if (e != cudaSuccess) return fail("step kernel launch failed: %s", cudaGetErrorString(e));
     h->launches += 1;
     h->env_steps += (uint64_t)h->n;
@@ -375,6 +409,9 @@ int32_t os2r_create_tuned(const os2r_model *model, const os2r_task_cfg *task, in
     h->model = *model; h->task = *task; h->precision = precision; h->device = device;
     h->n = n_envs; h->first_env_id = first_env_id; h->seed = seed;
     h->rows = model->n_dof + 3 * model->n_contacts;
+    // the kernels specialised on the shipped models' structure run when the model has exactly that structure
+    model_signature(*model, &h->sig_j, &h->sig_c);
+    if (tune.disable_specialisation) { h->sig_j = generic_joint_signature(model->n_dof); h->sig_c = generic_contact_signature(model->n_contacts); }
     build_model_dev<float>(*model, tune, h->m32);
     build_model_dev<double>(*model, tune, h->m64);
     memset(&h->taskdev, 0, sizeof(h->taskdev));
@@ -382,6 +419,7 @@ int32_t os2r_create_tuned(const os2r_model *model, const os2r_task_cfg *task, in
     for (int i = 0; i < model->n_dof; ++i) { h->taskdev.nominal_damping[i] = model->damping[i]; h->taskdev.nominal_friction[i] = model->friction[i]; }
     for (int c = 0; c < model->n_contacts; ++c) h->taskdev.nominal_mu[c] = model->contact_mu[c];
     for (int r = 0; r < OS2R_N_ROLES; ++r) h->taskdev.role_dof[r] = model->role_dof[r];
+    for (int k = 0; k < task->obs_dim && k < OS2R_MAX_OBS; ++k) h->taskdev.obs_scale[k] = 2.0 / (task->obs_high[k] - task->obs_low[k]);
     h->taskdev.n_dof = model->n_dof; h->taskdev.n_contacts = model->n_contacts;
 
     const size_t esz = precision == 32 ? sizeof(float) : sizeof(double);
@@ -400,7 +438,7 @@ int32_t os2r_create_tuned(const os2r_model *model, const os2r_task_cfg *task, in
     if ((e = cudaMalloc(&h->cls, n_envs)) != cudaSuccess) return cleanup("cudaMalloc(cls)", e);
     if ((e = cudaMalloc(&h->stats, sizeof(StatsDev))) != cudaSuccess) return cleanup("cudaMalloc(stats)", e);
     if ((e = cudaMemset(h->stats, 0, sizeof(StatsDev))) != cudaSuccess) return cleanup("cudaMemset(stats)", e);
-    e = prepare_step(h->build, model->n_dof, model->n_contacts, h->block);
+    e = prepare_step(h->build, model->n_dof, model->n_contacts, h->block, h->sig_j, h->sig_c);
     if (e != cudaSuccess) return cleanup("cudaFuncSetAttribute(step kernel shared memory)", e);
     if (precision == 32) { carve<float>(h, h->s32); e = launch_init<float>(h->taskdev, h->s32, model->gravity_z, 0); }
     else { carve<double>(h, h->s64); e = launch_init<double>(h->taskdev, h->s64, model->gravity_z, 0); }
@@ -713,13 +751,25 @@ int64_t os2r_num_envs(const os2r_env *h) { return h ? h->n : 0; }
 int32_t os2r_obs_dim(const os2r_env *h) { return h ? h->task.obs_dim : 0; }
 int64_t os2r_kernel_launches(const os2r_env *h) { return h ? h->launches : 0; }
 
+int32_t os2r_model_signature(const os2r_model *model, uint32_t *joints, uint32_t *contacts, int32_t *specialised) {
+    if (!model) return fail("os2r_model_signature: null model");
+    if (model->n_dof < 1 || model->n_dof > OS2R_MAX_DOF || model->n_contacts < 0 || model->n_contacts > OS2R_MAX_CONTACTS)
+        return fail("os2r_model_signature: model shape out of range");
+    uint32_t sj = 0, sc = 0, kj = 0, kc = 0;
+    model_signature(*model, &sj, &sc);
+    if (joints) *joints = sj;
+    if (contacts) *contacts = sc;
+    if (specialised) *specialised = (shipped_signature(model->n_dof, model->n_contacts, &kj, &kc) && kj == sj && kc == sc) ? 1 : 0;
+    return 0;
+}
+
 int32_t os2r_kernel_info(const os2r_env *h, int32_t *block_threads, int32_t *grid_blocks, int32_t *regs_per_thread,
                          int32_t *local_bytes_per_thread, int32_t *resident_blocks_per_sm, int32_t *envs_per_thread) {
     if (!h) return fail("os2r_kernel_info: null handle");
     DeviceGuard guard(h->device);
     cudaFuncAttributes a;
     int resident = 0, epb = h->block;
-    cudaError_t e = step_kernel_attributes(h->build, h->model.n_dof, h->model.n_contacts, h->block, h->m32.any_damping != 0, &a, &resident, &epb);
+    cudaError_t e = step_kernel_attributes(h->build, h->model.n_dof, h->model.n_contacts, h->block, h->m32.any_damping != 0, h->sig_j, h->sig_c, &a, &resident, &epb);
     if (e != cudaSuccess) return fail("cudaFuncGetAttributes failed: %s", cudaGetErrorString(e));
     if (block_threads) *block_threads = h->block;
     if (grid_blocks) *grid_blocks = (int32_t)((h->n + epb - 1) / epb);

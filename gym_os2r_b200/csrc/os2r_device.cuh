@@ -65,6 +65,7 @@ struct TaskDev {                 // epilogue + reset configuration (fp64: evalua
     double nominal_damping[OS2R_MAX_DOF];
     double nominal_friction[OS2R_MAX_DOF];
     double nominal_mu[OS2R_MAX_CONTACTS];
+    double obs_scale[OS2R_MAX_OBS];   // 2 / (obs_high - obs_low): the fp32 build normalises with one FMA instead of a division
     int32_t role_dof[OS2R_N_ROLES];
     int32_t n_dof, n_contacts;
 };
@@ -389,7 +390,23 @@ struct EnvRegs {                 // hot per-thread state
     V gz;                        // gravity z (negative)
 };
 
-template <typename V, int N, int NC, bool DAMPED, typename ColdT>
+// ------------------------------------------------------------------------------------------------
+// structure signature of a model: which entries of its constant tables are exactly 0 / 1, found on the host
+// (model_signature in os2r_capi.cu, |x| <= 1e-15 counts as 0). The forward pass is instantiated on it, so that a joint
+// whose frame coincides with its parent's (tree_R = 1), differs by a turn about the joint axis x, about y or about z, or whose
+// origin / a proxy's centre has zero components, skips the multiplications by those constants (they live in the constant
+// bank: the compiler cannot). Joints: 6 bits each, bits 0-2 = kind of tree_R, bits 3-5 = non-zero components of tree_p;
+// proxies: 3 bits each = non-zero components of contact_pos. The all-general signature runs any model.
+// ------------------------------------------------------------------------------------------------
+enum { OS2R_TREE_GENERAL = 0, OS2R_TREE_IDENTITY = 1, OS2R_TREE_XTURN = 2, OS2R_TREE_ZTURN = 3, OS2R_TREE_YTURN = 4 };
+__host__ __device__ constexpr uint32_t generic_joint_signature(int n) {
+    return n ? ((generic_joint_signature(n - 1) << 6) | (7u << 3) | OS2R_TREE_GENERAL) : 0u;
+}
+__host__ __device__ constexpr uint32_t generic_contact_signature(int nc) {
+    return nc ? ((generic_contact_signature(nc - 1) << 3) | 7u) : 0u;
+}
+
+template <typename V, int N, int NC, bool DAMPED, uint32_t SJ, uint32_t SC, typename ColdT>
 __device__ __forceinline__ void physics_iteration(const ModelDev<typename VT<V>::S> &M, EnvRegs<V, N> &E, const ColdT &C) {
     using SL = ColdSlots<N, NC>;
     using T = typename VT<V>::S;
@@ -453,24 +470,60 @@ __device__ __forceinline__ void physics_iteration(const ModelDev<typename VT<V>:
 #pragma unroll
                 for (int k = 0; k < 9; ++k) A[k] = V(M.tree_R[0][k]);
             } else {
+                const uint32_t tree_kind = (SJ >> (6 * i)) & 7u, p_mask = (SJ >> (6 * i + 3)) & 7u;   // constants after unrolling
                 const T *tp = M.tree_p[i];
-                V dp[3], wd[3];
+                if (p_mask) {
+                    V dp[3], wd[3];
 #pragma unroll
-                for (int r = 0; r < 3; ++r) dp[r] = R[3 * r] * tp[0] + R[3 * r + 1] * tp[1] + R[3 * r + 2] * tp[2];
-                // acceleration of the next joint origin, carried by the parent body: ap += al x dp + w x (w x dp)
-                OS2R_CROSS(wd, w, dp);
-                OS2R_CROSS_ACC(ap, al, dp);
-                OS2R_CROSS_ACC(ap, w, wd);
+                    for (int r = 0; r < 3; ++r) {
+                        V acc = V(0);
+                        bool first = true;
 #pragma unroll
-                for (int r = 0; r < 3; ++r) p[r] += dp[r];
+                        for (int c = 0; c < 3; ++c)
+                            if ((p_mask >> c) & 1u) { acc = first ? R[3 * r + c] * tp[c] : fma_t(R[3 * r + c], V(tp[c]), acc); first = false; }
+                        dp[r] = acc;
+                    }
+                    // acceleration of the next joint origin, carried by the parent body: ap += al x dp + w x (w x dp)
+                    OS2R_CROSS(wd, w, dp);
+                    OS2R_CROSS_ACC(ap, al, dp);
+                    OS2R_CROSS_ACC(ap, w, wd);
+#pragma unroll
+                    for (int r = 0; r < 3; ++r) p[r] += dp[r];
+                }
                 const T *tR = M.tree_R[i];
+                if (tree_kind == OS2R_TREE_GENERAL) {
 #pragma unroll
-                for (int r = 0; r < 3; ++r)
+                    for (int r = 0; r < 3; ++r)
 #pragma unroll
-                    for (int c = 0; c < 3; ++c)
-                        A[3 * r + c] = R[3 * r] * tR[c] + R[3 * r + 1] * tR[3 + c] + R[3 * r + 2] * tR[6 + c];
+                        for (int c = 0; c < 3; ++c)
+                            A[3 * r + c] = R[3 * r] * tR[c] + R[3 * r + 1] * tR[3 + c] + R[3 * r + 2] * tR[6 + c];
+                } else if (tree_kind == OS2R_TREE_ZTURN) {      // tree_R = turn about z: third column unchanged
+#pragma unroll
+                    for (int r = 0; r < 3; ++r) {
+                        A[3 * r] = R[3 * r] * tR[0] + R[3 * r + 1] * tR[3];
+                        A[3 * r + 1] = R[3 * r] * tR[1] + R[3 * r + 1] * tR[4];
+                        A[3 * r + 2] = R[3 * r + 2];
+                    }
+                } else if (tree_kind == OS2R_TREE_YTURN) {      // tree_R = turn about y: second column unchanged
+#pragma unroll
+                    for (int r = 0; r < 3; ++r) {
+                        A[3 * r] = R[3 * r] * tR[0] + R[3 * r + 2] * tR[6];
+                        A[3 * r + 1] = R[3 * r + 1];
+                        A[3 * r + 2] = R[3 * r] * tR[2] + R[3 * r + 2] * tR[8];
+                    }
+                } else {                                         // identity, or a turn about x (folded into s, c below)
+#pragma unroll
+                    for (int k = 0; k < 9; ++k) A[k] = R[k];
+                }
             }
-            const V s = sn[i], c = cs[i];
+            V s = sn[i], c = cs[i];
+            if (i > 0 && ((SJ >> (6 * i)) & 7u) == OS2R_TREE_XTURN) {
+                // tree_R = turn about the joint axis by phi: R Rx(phi) Rx(q) = R Rx(phi + q) — the angle addition on
+                // (sin, cos) with the table's own cos phi = tree_R[4], sin phi = tree_R[7] replaces the 3x3 product
+                const T cphi = M.tree_R[i][4], sphi = M.tree_R[i][7];
+                const V c2 = c * cphi - s * sphi, s2 = s * cphi + c * sphi;
+                c = c2; s = s2;
+            }
 #pragma unroll
             for (int r = 0; r < 3; ++r) {
                 const V a1 = A[3 * r + 1], a2 = A[3 * r + 2];
@@ -548,9 +601,15 @@ __device__ __forceinline__ void physics_iteration(const ModelDev<typename VT<V>:
             for (int k = 0; k < NC; ++k) {
                 if (M.contact_body[k] == i) {
                     const T *cp = M.contact_pos[k];
+                    const uint32_t c_mask = (SC >> (3 * k)) & 7u;
 #pragma unroll
-                    for (int r = 0; r < 3; ++r)
-                        C(SL::CX + 3 * k + r) = p[r] + R[3 * r] * cp[0] + R[3 * r + 1] * cp[1] + R[3 * r + 2] * cp[2];
+                    for (int r = 0; r < 3; ++r) {
+                        V acc = p[r];
+#pragma unroll
+                        for (int cc = 0; cc < 3; ++cc)
+                            if ((c_mask >> cc) & 1u) acc = fma_t(R[3 * r + cc], V(cp[cc]), acc);
+                        C(SL::CX + 3 * k + r) = acc;
+                    }
                 }
             }
         }
@@ -841,8 +900,12 @@ __device__ inline double np_mod_pos(double x, double y) {
     return r;
 }
 
-// raw[] (masked, wrapped) and normalised obs[]; returns done-by-task
-template <int N>
+// raw[] (masked, wrapped) and normalised obs[]; returns done-by-task.
+// FAST (the fp32 product build; the observation leaves the device as float32 either way): position columns are
+// normalised with the host's 2 / (high - low) in one fp64 FMA instead of an fp64 division, velocity columns through the
+// fp32 tanhf (<= 2 ulp of a float) instead of the fp64 tanh — together 8 % of the warp-time of a contact-free step
+// (profiles/r2_step_kernel_fresh_by_region.txt). Termination is decided on the RAW fp64 values in both builds.
+template <int N, bool FAST = false>
 __device__ inline bool observe(const TaskDev &K, const double *q, const double *v, const double *a_old,
                                double *obs) {
     const os2r_task_cfg &C = K.cfg;
@@ -863,8 +926,8 @@ __device__ inline bool observe(const TaskDev &K, const double *q, const double *
         done |= !(x >= C.done_low[k]) || !(x <= C.done_high[k]);
         double o = x;
         if (C.normalized) {
-            if (kind == OS2R_OBS_VEL) o = tanh(0.05 * x);
-            else o = 2 * (x - C.obs_low[k]) / (C.obs_high[k] - C.obs_low[k]) - 1;
+            if (kind == OS2R_OBS_VEL) o = FAST ? (double)tanhf((float)(0.05 * x)) : tanh(0.05 * x);
+            else o = FAST ? fma(x - C.obs_low[k], K.obs_scale[k], -1.0) : 2 * (x - C.obs_low[k]) / (C.obs_high[k] - C.obs_low[k]) - 1;
         }
         obs[k] = o;
     }

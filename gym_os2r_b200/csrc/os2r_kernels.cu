@@ -52,7 +52,7 @@ __device__ __noinline__ int reset_env_global(const TaskDev &K, StateDev<T> &S, i
 #pragma unroll
         for (int i = 0; i < N; ++i) qs[i] = (double)S.q_hi[i * NE + e] + (double)S.q_lo[i * NE + e];
         double o[OS2R_MAX_OBS];
-        observe<N>(K, qs, v, a_old, o);
+        observe<N, sizeof(T) == 4>(K, qs, v, a_old, o);
         for (int k = 0; k < K.cfg.obs_dim; ++k) obs_row[k] = (float)o[k];
     }
     return idx;
@@ -173,7 +173,8 @@ __device__ __forceinline__ V from_halves(const float (&x)[VT<V>::LANES]) {
 // and one block per SM at 255 registers, was measured in round 2 — 106 vs 89 us per step, profiles/r2_step_kernel_pair_*
 // — and dropped: with 7 warps per SM the kernel is bound by dependent-issue latency, not by issue slots. The packed
 // instructions are used INSIDE an env instead: os2r_device.cuh, forward pass.)
-template <typename V, int N, int NC, int BLOCK, bool DAMPED, int MINB>
+// SJ / SC: the model's structure signature (os2r_device.cuh): the shipped URDFs' own, or the all-general one.
+template <typename V, int N, int NC, int BLOCK, bool DAMPED, int MINB, uint32_t SJ, uint32_t SC>
 __global__ void __launch_bounds__(BLOCK, MINB)
 step_kernel(const __grid_constant__ ModelDev<typename VT<V>::S> M, const __grid_constant__ TaskDev K,
             StateDev<typename VT<V>::S> S, const __grid_constant__ StepIO IO, StatsDev *stats) {
@@ -324,7 +325,7 @@ step_kernel(const __grid_constant__ ModelDev<typename VT<V>::S> M, const __grid_
         // Keep the block's warps in phase: all warps of an SM run the same ~40 KB loop body, and warps that drift
         // apart thrash the instruction caches.
         __syncthreads();
-        physics_iteration<V, N, NC, DAMPED, Cold<V, BLOCK>>(M, E, C);
+        physics_iteration<V, N, NC, DAMPED, SJ, SC, Cold<V, BLOCK>>(M, E, C);
     }
 #ifdef OS2R_CHECKED
     OS2R_CHECK(half_of(C(SL::COUNT), 0) == (T)12345.0f, 4);
@@ -357,7 +358,7 @@ step_kernel(const __grid_constant__ ModelDev<typename VT<V>::S> M, const __grid_
         }
         const double a0[2] = {(double)actx, (double)acty};
         double o[OS2R_MAX_OBS];
-        const bool task_done = observe<N>(K, q, v, a_old, o);
+        const bool task_done = observe<N, sizeof(T) == 4>(K, q, v, a_old, o);
         const double r = finite ? reward_fn(K.cfg, o, a0, a_old) : 0.0;
         const int D = K.cfg.obs_dim;
         int cause = (task_done && finite) ? 1 : 0;
@@ -490,48 +491,71 @@ struct StepFn {          // one instantiation of the step kernel
     int envs_per_block;
 };
 
-template <typename V, int N, int NC, int BLOCK, bool DAMPED>
+// Structure signatures of the shipped models (gym_os2r_b200/models/assets/*.urdf), as model_signature() computes
+// them: monopod-simple (2 joints), monopod-fixed (3), monopod-fixed_hip (4), monopod (5, with and without the bracket
+// proxy). tests/test_capi_cpu.py::test_shipped_models_run_the_specialised_kernels keeps the table honest; any other
+// model runs the all-general instantiation.
+template <int N, int NC> struct Shipped { static constexpr uint32_t J = 0xffffffffu, C = 0xffffffffu; };   // none
+template <> struct Shipped<2, 3> { static constexpr uint32_t J = OS2R_SHIPPED_J23, C = OS2R_SHIPPED_C23; };
+template <> struct Shipped<3, 3> { static constexpr uint32_t J = OS2R_SHIPPED_J33, C = OS2R_SHIPPED_C33; };
+template <> struct Shipped<4, 3> { static constexpr uint32_t J = OS2R_SHIPPED_J43, C = OS2R_SHIPPED_C43; };
+template <> struct Shipped<5, 3> { static constexpr uint32_t J = OS2R_SHIPPED_J53, C = OS2R_SHIPPED_C53; };
+template <> struct Shipped<5, 4> { static constexpr uint32_t J = OS2R_SHIPPED_J54, C = OS2R_SHIPPED_C54; };
+
+template <typename V, int N, int NC, int BLOCK, bool DAMPED, bool SPECIAL>
 StepFn step_fn() {
     // two resident 7-warp blocks per SM for the float build (128 registers per thread); everything else: no occupancy target
     constexpr int MINB = (VT<V>::LANES == 1 && sizeof(typename VT<V>::S) == 4 && BLOCK == OS2R_BLOCK_WIDE) ? 2 : 1;
-    return StepFn{(const void *)step_kernel<V, N, NC, BLOCK, DAMPED, MINB>, step_smem_bytes<V, N, NC, BLOCK>(), BLOCK * VT<V>::LANES};
+    constexpr uint32_t SJ = SPECIAL ? Shipped<N, NC>::J : generic_joint_signature(N);
+    constexpr uint32_t SC = SPECIAL ? Shipped<N, NC>::C : generic_contact_signature(NC);
+    return StepFn{(const void *)step_kernel<V, N, NC, BLOCK, DAMPED, MINB, SJ, SC>, step_smem_bytes<V, N, NC, BLOCK>(), BLOCK * VT<V>::LANES};
 }
 template <typename V, int N, int NC, int BLOCK>
-StepFn step_fn_d(bool damped) {
+StepFn step_fn_d(bool damped, uint32_t sj, uint32_t sc) {
+    // the shipped models are undamped: the specialised kernels exist for the builds those models run
+    const bool special = sj == Shipped<N, NC>::J && sc == Shipped<N, NC>::C;
     // the fp64 verification build keeps one (damped) instantiation; with zero damping its second factor equals the first
-    if (sizeof(typename VT<V>::S) == 8 || damped) return step_fn<V, N, NC, BLOCK, true>();
-    if constexpr (sizeof(typename VT<V>::S) == 4) return step_fn<V, N, NC, BLOCK, false>();
-    return StepFn{nullptr, 0, 0};
+    if constexpr (sizeof(typename VT<V>::S) == 8) {
+        return special ? step_fn<V, N, NC, BLOCK, true, true>() : step_fn<V, N, NC, BLOCK, true, false>();
+    } else {
+        if (damped) return step_fn<V, N, NC, BLOCK, true, false>();
+        return special ? step_fn<V, N, NC, BLOCK, false, true>() : step_fn<V, N, NC, BLOCK, false, false>();
+    }
 }
 template <typename V>
-cudaError_t pick(int n_dof, int n_contacts, int block, bool damped, StepFn *out) {
+cudaError_t pick(int n_dof, int n_contacts, int block, bool damped, uint32_t sj, uint32_t sc, StepFn *out) {
     if (block == OS2R_BLOCK_WIDE) {
         if constexpr (sizeof(typename VT<V>::S) == 4) {
-            OS2R_DISPATCH(n_dof, n_contacts, *out = (step_fn_d<V, N_, NC_, OS2R_BLOCK_WIDE>(damped)));
+            OS2R_DISPATCH(n_dof, n_contacts, *out = (step_fn_d<V, N_, NC_, OS2R_BLOCK_WIDE>(damped, sj, sc)));
             return cudaSuccess;
         }
         return cudaErrorInvalidValue;
     }
     if (block != OS2R_BLOCK) return cudaErrorInvalidValue;
-    OS2R_DISPATCH(n_dof, n_contacts, *out = (step_fn_d<V, N_, NC_, OS2R_BLOCK>(damped)));
+    OS2R_DISPATCH(n_dof, n_contacts, *out = (step_fn_d<V, N_, NC_, OS2R_BLOCK>(damped, sj, sc)));
     return cudaSuccess;
 }
-cudaError_t pick_build(int build, int n_dof, int n_contacts, int block, bool damped, StepFn *out) {
+cudaError_t pick_build(int build, int n_dof, int n_contacts, int block, bool damped, uint32_t sj, uint32_t sc, StepFn *out) {
     switch (build) {
-    case OS2R_BUILD_F32: return pick<float>(n_dof, n_contacts, block, damped, out);
-    case OS2R_BUILD_F64: return pick<double>(n_dof, n_contacts, block, true, out);
+    case OS2R_BUILD_F32: return pick<float>(n_dof, n_contacts, block, damped, sj, sc, out);
+    case OS2R_BUILD_F64: return pick<double>(n_dof, n_contacts, block, true, sj, sc, out);
     default: return cudaErrorInvalidValue;
     }
 }
 
 }  // namespace
 
+bool shipped_signature(int n_dof, int n_contacts, uint32_t *sj, uint32_t *sc) {
+    auto probe = [&]() -> cudaError_t { OS2R_DISPATCH(n_dof, n_contacts, (*sj = Shipped<N_, NC_>::J, *sc = Shipped<N_, NC_>::C)); return cudaSuccess; };
+    return probe() == cudaSuccess;
+}
+
 template <typename T>
-cudaError_t launch_step(int build, int n_dof, int n_contacts, int block, const ModelDev<T> &M, const TaskDev &K,
-                        const StateDev<T> &S, const StepIO &io, StatsDev *stats, cudaStream_t stream) {
+cudaError_t launch_step(int build, int n_dof, int n_contacts, int block, uint32_t sj, uint32_t sc, const ModelDev<T> &M,
+                        const TaskDev &K, const StateDev<T> &S, const StepIO &io, StatsDev *stats, cudaStream_t stream) {
     if ((build == OS2R_BUILD_F64) != (sizeof(T) == 8)) return cudaErrorInvalidValue;
     StepFn f;
-    cudaError_t e = pick_build(build, n_dof, n_contacts, block, M.any_damping != 0, &f);
+    cudaError_t e = pick_build(build, n_dof, n_contacts, block, M.any_damping != 0, sj, sc, &f);
     if (e != cudaSuccess) return e;
     // blocks that need more than 48 KB of dynamic shared memory were opted in by prepare_step (once per handle,
     // on the handle's device: the attribute is per device, a process can hold handles on several GPUs)
@@ -554,10 +578,10 @@ cudaError_t launch_init(const TaskDev &K, const StateDev<T> &S, double nominal_g
 
 // Opt the step kernels this handle can launch (damped and undamped build) into their dynamic shared memory size on the
 // CURRENT device. Called by os2r_create under its device guard.
-cudaError_t prepare_step(int build, int n_dof, int n_contacts, int block) {
+cudaError_t prepare_step(int build, int n_dof, int n_contacts, int block, uint32_t sj, uint32_t sc) {
     for (int damped = 0; damped < 2; ++damped) {
         StepFn f;
-        cudaError_t e = pick_build(build, n_dof, n_contacts, block, damped != 0, &f);
+        cudaError_t e = pick_build(build, n_dof, n_contacts, block, damped != 0, sj, sc, &f);
         if (e != cudaSuccess) return e;
         if (f.smem > 48 * 1024) {
             e = cudaFuncSetAttribute(f.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f.smem);
@@ -567,10 +591,10 @@ cudaError_t prepare_step(int build, int n_dof, int n_contacts, int block) {
     return cudaSuccess;
 }
 
-cudaError_t step_kernel_attributes(int build, int n_dof, int n_contacts, int block, bool damped, cudaFuncAttributes *attr,
-                                   int *blocks_per_sm, int *envs_per_block) {
+cudaError_t step_kernel_attributes(int build, int n_dof, int n_contacts, int block, bool damped, uint32_t sj, uint32_t sc,
+                                   cudaFuncAttributes *attr, int *blocks_per_sm, int *envs_per_block) {
     StepFn f;
-    cudaError_t e = pick_build(build, n_dof, n_contacts, block, damped, &f);
+    cudaError_t e = pick_build(build, n_dof, n_contacts, block, damped, sj, sc, &f);
     if (e != cudaSuccess) return e;
     e = cudaFuncGetAttributes(attr, f.fn);
     if (e != cudaSuccess) return e;
@@ -599,7 +623,7 @@ cudaError_t launch_fma_peak(float *out, int blocks, int iters, cudaStream_t stre
 }
 
 #define OS2R_INSTANTIATE(T)                                                                                   \
-    template cudaError_t launch_step<T>(int, int, int, int, const ModelDev<T> &, const TaskDev &, const StateDev<T> &, \
+    template cudaError_t launch_step<T>(int, int, int, int, uint32_t, uint32_t, const ModelDev<T> &, const TaskDev &, const StateDev<T> &, \
                                         const StepIO &, StatsDev *, cudaStream_t);                            \
     template cudaError_t launch_reset<T>(int, int, const TaskDev &, const StateDev<T> &, const uint8_t *,     \
                                          float *, cudaStream_t);                                              \

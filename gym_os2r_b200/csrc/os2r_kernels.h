@@ -13,6 +13,18 @@
 #define OS2R_BLOCK_WIDE 224
 #endif
 
+// Structure signatures (os2r_device.cuh) of the shipped URDFs, as os2r_model_signature reports them.
+#define OS2R_SHIPPED_J23 0xab8u
+#define OS2R_SHIPPED_C23 0x120u
+#define OS2R_SHIPPED_J33 0x2a6f8u
+#define OS2R_SHIPPED_C33 0x120u
+#define OS2R_SHIPPED_J43 0xa9b138u
+#define OS2R_SHIPPED_C43 0x120u
+#define OS2R_SHIPPED_J53 0x2a290138u
+#define OS2R_SHIPPED_C53 0x120u
+#define OS2R_SHIPPED_J54 0x2a290138u
+#define OS2R_SHIPPED_C54 0x906u
+
 // builds of the step kernel
 #define OS2R_BUILD_F32 0    // fp32, one env per thread: the product path
 #define OS2R_BUILD_F64 2    // fp64, one env per thread (verification)
@@ -21,17 +33,19 @@ namespace os2r {
 
 int step_block_threads(int build, int64_t n_envs, int sm_count);
 template <typename T>
-cudaError_t launch_step(int build, int n_dof, int n_contacts, int block, const ModelDev<T> &M, const TaskDev &K,
-                        const StateDev<T> &S, const StepIO &io, StatsDev *stats, cudaStream_t stream);
+cudaError_t launch_step(int build, int n_dof, int n_contacts, int block, uint32_t sj, uint32_t sc, const ModelDev<T> &M,
+                        const TaskDev &K, const StateDev<T> &S, const StepIO &io, StatsDev *stats, cudaStream_t stream);
 template <typename T>
 cudaError_t launch_reset(int n_dof, int n_contacts, const TaskDev &K, const StateDev<T> &S, const uint8_t *mask,
                          float *obs, cudaStream_t stream);
 template <typename T>
 cudaError_t launch_init(const TaskDev &K, const StateDev<T> &S, double nominal_gz, cudaStream_t stream);
-cudaError_t prepare_step(int build, int n_dof, int n_contacts, int block);
+cudaError_t prepare_step(int build, int n_dof, int n_contacts, int block, uint32_t sj, uint32_t sc);
+// signature the specialised kernels of this (joints, proxies) shape were built for
+bool shipped_signature(int n_dof, int n_contacts, uint32_t *sj, uint32_t *sc);
 bool supported_shape(int n_dof, int n_contacts);
-cudaError_t step_kernel_attributes(int build, int n_dof, int n_contacts, int block, bool damped, cudaFuncAttributes *attr,
-                                   int *blocks_per_sm, int *envs_per_block);
+cudaError_t step_kernel_attributes(int build, int n_dof, int n_contacts, int block, bool damped, uint32_t sj, uint32_t sc,
+                                   cudaFuncAttributes *attr, int *blocks_per_sm, int *envs_per_block);
 cudaError_t read_check_counters(unsigned long long out[8], bool clear);
 cudaError_t launch_fma_peak(float *out, int blocks, int iters, cudaStream_t stream);
 

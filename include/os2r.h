@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define OS2R_ABI_VERSION 8
+#define OS2R_ABI_VERSION 9
 
 #define OS2R_MAX_DOF 5
 #define OS2R_MAX_CONTACTS 6
@@ -172,7 +172,8 @@ typedef struct os2r_tuning {
                                   <= 0: default 0.002                                                              */
     int32_t force_block;       /* threads per block of the step kernel (64, or 224 for the fp32 builds); 0: chosen
                                   from the batch size                                                             */
-    int32_t _reserved0;
+    int32_t disable_specialisation; /* 1: run the all-general step kernel even when the model has the structure of a
+                                  shipped URDF (verification of the specialised kernels)                          */
     int32_t disable_root_fold; /* 1: run the general per-body code for the yaw pivot (verification of the fold)  */
     int32_t _pad;
 } os2r_tuning;
@@ -276,6 +277,10 @@ int64_t os2r_kernel_launches(const os2r_env *env); /* kernels launched by this h
 int32_t os2r_kernel_info(const os2r_env *env, int32_t *block_threads, int32_t *grid_blocks,
                          int32_t *regs_per_thread, int32_t *local_bytes_per_thread,
                          int32_t *resident_blocks_per_sm, int32_t *envs_per_thread);
+/* Structure signature of a model (which constant-table entries are exactly 0 / 1; gym_os2r_b200/csrc/os2r_device.cuh)
+ * and whether this library carries step kernels specialised on it (the shipped URDFs: yes; any other model runs the
+ * all-general kernels). Host only: needs no GPU. Any out pointer may be NULL. */
+int32_t os2r_model_signature(const os2r_model *model, uint32_t *joints, uint32_t *contacts, int32_t *specialised);
 /* Violation counters of the CHECKED build (`make -C gym_os2r_b200/csrc libos2r_checked.so`: the step kernel validates
  * its lane-sort permutation, env indices, terminal-record capacity and a shared-memory guard word; violations are
  * counted, not trapped). out8[0..4] = counts (see os2r_kernels.cu), out8[7] = 1 when the loaded library was built

@@ -82,6 +82,28 @@ def test_create_rejects_bad_arguments(lib):
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason='checks the no-GPU failure mode')
+def test_shipped_models_run_the_specialised_kernels(lib):
+    """os2r_model_signature (host only): the four shipped URDFs have exactly the structure signatures the specialised
+    step kernels were instantiated for (os2r_kernels.h OS2R_SHIPPED_*); a model with another structure does not, and
+    runs the all-general kernels."""
+    from helpers import make_config
+    seen = {}
+    for mode in ('simple', 'fixed', 'fixed_hip', 'free_hip'):
+        task, cm, cfg = make_config(mode, reward='StraightV1' if mode == 'simple' else 'BalancingV1')
+        j, c, sp = C.c_uint32(), C.c_uint32(), C.c_int32()
+        assert lib.os2r_model_signature(C.byref(cm.struct), C.byref(j), C.byref(c), C.byref(sp)) == 0
+        assert sp.value == 1, (mode, hex(j.value), hex(c.value))
+        seen[mode] = (j.value, c.value)
+    assert len(set(seen.values())) == 4
+    # tilt one joint frame: no longer a shipped structure
+    task, cm, cfg = make_config('fixed_hip')
+    other = type(cm.struct)(); C.memmove(C.byref(other), C.byref(cm.struct), C.sizeof(other))
+    other.tree_p[2][2] = 0.01
+    j, c, sp = C.c_uint32(), C.c_uint32(), C.c_int32()
+    assert lib.os2r_model_signature(C.byref(other), C.byref(j), C.byref(c), C.byref(sp)) == 0
+    assert sp.value == 0 and j.value != seen['fixed_hip'][0]
+
+
 def test_no_cpu_fallback(lib):
     """Without a CUDA device the product path must fail loudly, never fall back to a CPU implementation."""
     task, cm, cfg = make_config('fixed_hip')

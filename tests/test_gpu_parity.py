@@ -146,6 +146,36 @@ def test_root_spin_shortcut_matches_general_path():
         assert np.abs(out[0][:, n:2 * n] - out[1][:, n:2 * n]).max() < 1e-8, mode
 
 
+def test_specialised_kernels_match_the_general_ones():
+    """The step kernels instantiated on the shipped models' structure signature (os2r_device.cuh: joints whose frame is
+    the parent's up to a turn about x / y / z, zero components of joint origins and proxy centres) skip multiplications
+    by constants that are exactly 0 or 1 — |x| <= 1e-15 counts as 0, which drops terms of the order 1e-19 the URDFs'
+    literal rpy leave behind. With `disable_specialisation` the same model runs the all-general kernel: fp64 agrees to
+    rounding, fp32 to a few ulp of the state, in every mode, with and without contact."""
+    N = 512
+    rng = np.random.RandomState(37)
+    for mode, reward in (('simple', 'StraightV1'), ('fixed', 'BalancingV1'), ('fixed_hip', 'BalancingV1'), ('free_hip', 'HoppingV1')):
+        task, cm, cfg = make_config(mode, reward=reward, randomize_params=True, reset_randomized=mode != 'simple')
+        st = _random_state(cm, N, rng, mode != 'simple')
+        a = rng.uniform(-1, 1, (N, 2)).astype(np.float32)
+        n = cm.n_dof
+        for prec, tq, tv in ((64, 1e-11, 1e-9), (32, 2e-6, 2e-3)):
+            out = []
+            for disable in (False, True):
+                eng = Engine(cm, cfg, N, seed=3, precision=prec, tuning={'disable_specialisation': int(disable)})
+                eng.reset()
+                eng.set_state(st)
+                for _ in range(3):
+                    eng.step(torch.as_tensor(a, device='cuda'))
+                out.append(eng.get_state())
+                eng.close()
+            dq = np.abs(out[0][:, :n] - out[1][:, :n])
+            dv = np.abs(out[0][:, n:2 * n] - out[1][:, n:2 * n])
+            assert np.median(dq.max(1)) < tq and np.median(dv.max(1)) < tv, (mode, prec, dq.max(), dv.max())
+            if prec == 64:
+                assert dq.max() < 1e-9 and dv.max() < 1e-7, (mode, dq.max(), dv.max())
+
+
 def test_contact_free_trajectory_simple():
     """BASELINE config 2a at its full size: `simple` mode (2 DoF, never touches the ground), 4096 envs, sinusoidal
     actions A = 0.1, f = (1.0, 1.7) Hz, random phases, 1000 env steps, PRODUCTION sweep tolerance: the fp32 kernel stays
