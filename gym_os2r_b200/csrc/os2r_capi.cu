@@ -132,9 +132,7 @@ void build_model_dev(const os2r_model &m, const os2r_tuning &tune, ModelDev<T> &
 // a turn about z in the normalised frames, and which components of tree_p / contact_pos are zero. |x| <= 1e-15 counts as
 // zero (the URDFs' literal rpy "1.57" leaves products of the order 1e-19 in entries that are structurally 0: they are
 // below half an ulp of the fp64 sum they would enter).
-void model_signature(const os2r_model &m, uint32_t *sj, uint32_t *sc) {
-    os2r_tuning tune;
-    memset(&tune, 0, sizeof(tune));
+void model_signature(const os2r_model &m, const os2r_tuning &tune, uint32_t *sj, uint32_t *sc) {
     ModelDev<double> d;
     build_model_dev<double>(m, tune, d);
     auto z = [](double x) { return fabs(x) <= 1e-15; };
@@ -156,8 +154,9 @@ void model_signature(const os2r_model &m, uint32_t *sj, uint32_t *sc) {
     for (int c = m.n_contacts - 1; c >= 0; --c) {
         uint32_t cm = 0;
         for (int k = 0; k < 3; ++k) if (!z(d.contact_pos[c][k])) cm |= 1u << k;
-        C = (C << 3) | cm;
+        C = (C << 6) | ((uint32_t)m.contact_body[c] << 3) | cm;
     }
+    J |= (d.root_spin ? 2u : 1u) << 30;
     *sj = J; *sc = C;
 }
 
@@ -410,7 +409,7 @@ int32_t os2r_create_tuned(const os2r_model *model, const os2r_task_cfg *task, in
     h->n = n_envs; h->first_env_id = first_env_id; h->seed = seed;
     h->rows = model->n_dof + 3 * model->n_contacts;
     // the kernels specialised on the shipped models' structure run when the model has exactly that structure
-    model_signature(*model, &h->sig_j, &h->sig_c);
+    model_signature(*model, tune, &h->sig_j, &h->sig_c);
     if (tune.disable_specialisation) { h->sig_j = generic_joint_signature(model->n_dof); h->sig_c = generic_contact_signature(model->n_contacts); }
     build_model_dev<float>(*model, tune, h->m32);
     build_model_dev<double>(*model, tune, h->m64);
@@ -756,7 +755,9 @@ int32_t os2r_model_signature(const os2r_model *model, uint32_t *joints, uint32_t
     if (model->n_dof < 1 || model->n_dof > OS2R_MAX_DOF || model->n_contacts < 0 || model->n_contacts > OS2R_MAX_CONTACTS)
         return fail("os2r_model_signature: model shape out of range");
     uint32_t sj = 0, sc = 0, kj = 0, kc = 0;
-    model_signature(*model, &sj, &sc);
+    os2r_tuning tune;
+    memset(&tune, 0, sizeof(tune));
+    model_signature(*model, tune, &sj, &sc);
     if (joints) *joints = sj;
     if (contacts) *contacts = sc;
     if (specialised) *specialised = (shipped_signature(model->n_dof, model->n_contacts, &kj, &kc) && kj == sj && kc == sc) ? 1 : 0;

@@ -396,14 +396,33 @@ struct EnvRegs {                 // hot per-thread state
 // whose frame coincides with its parent's (tree_R = 1), differs by a turn about the joint axis x, about y or about z, or whose
 // origin / a proxy's centre has zero components, skips the multiplications by those constants (they live in the constant
 // bank: the compiler cannot). Joints: 6 bits each, bits 0-2 = kind of tree_R, bits 3-5 = non-zero components of tree_p;
-// proxies: 3 bits each = non-zero components of contact_pos. The all-general signature runs any model.
+// bits 30-31: 0 = whether the root body is folded (ModelDev::root_spin) is read at run time, 1 = it is not, 2 = it is.
+// Proxies: 6 bits each, bits 0-2 = non-zero components of contact_pos, bits 3-5 = the body that carries the proxy
+// (7 = read ModelDev::contact_body at run time). Known at compile time, the root fold and the proxy -> body map cost no
+// warp-uniform branches and leave no dead code in the loop body (~3.5 KB of the 38 KB the 4-joint model's loop had,
+// against a 32 KB instruction cache). The all-general signature runs any model.
 // ------------------------------------------------------------------------------------------------
 enum { OS2R_TREE_GENERAL = 0, OS2R_TREE_IDENTITY = 1, OS2R_TREE_XTURN = 2, OS2R_TREE_ZTURN = 3, OS2R_TREE_YTURN = 4 };
 __host__ __device__ constexpr uint32_t generic_joint_signature(int n) {
     return n ? ((generic_joint_signature(n - 1) << 6) | (7u << 3) | OS2R_TREE_GENERAL) : 0u;
 }
 __host__ __device__ constexpr uint32_t generic_contact_signature(int nc) {
-    return nc ? ((generic_contact_signature(nc - 1) << 3) | 7u) : 0u;
+    return nc ? ((generic_contact_signature(nc - 1) << 6) | (7u << 3) | 7u) : 0u;
+}
+// proxy k rides on body i / the root body is folded: compile-time constants when the signature knows
+template <uint32_t SC, typename MT>
+__device__ __forceinline__ bool proxy_on_body(const MT &M, int k, int i) {
+    const uint32_t b = (SC >> (6 * k + 3)) & 7u;
+    return b == 7u ? M.contact_body[k] == i : (int)b == i;
+}
+template <uint32_t SC, typename MT>
+__device__ __forceinline__ bool joint_moves_proxy(const MT &M, int k, int i) {
+    const uint32_t b = (SC >> (6 * k + 3)) & 7u;
+    return b == 7u ? i <= M.contact_body[k] : i <= (int)b;
+}
+template <uint32_t SJ, typename MT>
+__device__ __forceinline__ bool root_folded(const MT &M) {
+    return (SJ >> 30) == 0u ? M.root_spin != 0 : (SJ >> 30) == 2u;
 }
 
 template <typename V, int N, int NC, bool DAMPED, uint32_t SJ, uint32_t SC, typename ColdT>
@@ -542,7 +561,7 @@ __device__ __forceinline__ void physics_iteration(const ModelDev<typename VT<V>:
             }
 #pragma unroll
             for (int r = 0; r < 3; ++r) w[r] += ax[i][r] * qd;
-            if (i == 0 && M.root_spin) {   // warp-uniform; ~130 instructions of body 0 become one FMA
+            if (i == 0 && root_folded<SJ>(M)) {   // ~130 instructions of body 0 become one FMA
                 Mm[0][0] = fma_t(V(M.root_mass_term), C(SL::MASS), V(M.root_inertia_term));
             } else {
             // COM offset and rotational inertia in world axes
@@ -599,9 +618,9 @@ __device__ __forceinline__ void physics_iteration(const ModelDev<typename VT<V>:
             // contact spheres carried by this body
 #pragma unroll
             for (int k = 0; k < NC; ++k) {
-                if (M.contact_body[k] == i) {
+                if (proxy_on_body<SC>(M, k, i)) {
                     const T *cp = M.contact_pos[k];
-                    const uint32_t c_mask = (SC >> (3 * k)) & 7u;
+                    const uint32_t c_mask = (SC >> (6 * k)) & 7u;
 #pragma unroll
                     for (int r = 0; r < 3; ++r) {
                         V acc = p[r];
@@ -735,7 +754,7 @@ __device__ __forceinline__ void physics_iteration(const ModelDev<typename VT<V>:
                 const V rr[3] = {x[0] - P[i][0], x[1] - P[i][1], x[2] - P[i][2]};
                 V jc[3];
                 OS2R_CROSS(jc, ax[i], rr);
-                const bool on = i <= M.contact_body[c];
+                const bool on = joint_moves_proxy<SC>(M, c, i);
                 J[0][i] = on ? jc[2] : V(0);
                 J[1][i] = on ? jc[0] : V(0);
                 J[2][i] = on ? jc[1] : V(0);

@@ -14,16 +14,16 @@
 #endif
 
 // Structure signatures (os2r_device.cuh) of the shipped URDFs, as os2r_model_signature reports them.
-#define OS2R_SHIPPED_J23 0xab8u
-#define OS2R_SHIPPED_C23 0x120u
-#define OS2R_SHIPPED_J33 0x2a6f8u
-#define OS2R_SHIPPED_C33 0x120u
-#define OS2R_SHIPPED_J43 0xa9b138u
-#define OS2R_SHIPPED_C43 0x120u
-#define OS2R_SHIPPED_J53 0x2a290138u
-#define OS2R_SHIPPED_C53 0x120u
-#define OS2R_SHIPPED_J54 0x2a290138u
-#define OS2R_SHIPPED_C54 0x906u
+#define OS2R_SHIPPED_J23 0x40000ab8u
+#define OS2R_SHIPPED_C23 0xc100u
+#define OS2R_SHIPPED_J33 0x4002a6f8u
+#define OS2R_SHIPPED_C33 0x14308u
+#define OS2R_SHIPPED_J43 0x80a9b138u
+#define OS2R_SHIPPED_C43 0x1c510u
+#define OS2R_SHIPPED_J53 0xaa290138u
+#define OS2R_SHIPPED_C53 0x24718u
+#define OS2R_SHIPPED_J54 0xaa290138u
+#define OS2R_SHIPPED_C54 0x91c616u
 
 // builds of the step kernel
 #define OS2R_BUILD_F32 0    // fp32, one env per thread: the product path

@@ -21,9 +21,11 @@ rows = list(csv.reader(raw.splitlines()))
 kname = rows[0][1]
 hdr = rows[1]
 data = rows[2:]
-m = re.search(r'step_kernel<(\w+), \(int\)(\d+), \(int\)(\d+), \(int\)(\d+), \(bool\)(\d), \(int\)(\d+)>', kname)
+m = re.search(r'step_kernel<(\w+), \(int\)(\d+), \(int\)(\d+), \(int\)(\d+), \(bool\)(\d), \(int\)(\d+)(?:, \(unsigned int\)(\d+), \(unsigned int\)(\d+))?>', kname)
 ty = {'float': 'f', 'double': 'd', 'f2': 'NS_2f2E'}[m.group(1).split('::')[-1]]
 mangled = f'step_kernelI{ty}Li{m.group(2)}ELi{m.group(3)}ELi{m.group(4)}ELb{m.group(5)}ELi{m.group(6)}E'
+if m.group(7):   # structure signature (round 2b)
+    mangled += f'Lj{m.group(7)}ELj{m.group(8)}E'
 with tempfile.TemporaryDirectory() as td:
     subprocess.check_call(['cuobjdump', '-xelf', 'all', os.path.join(ROOT, 'gym_os2r_b200', 'csrc', 'libos2r.so')], cwd=td,
                           stdout=subprocess.DEVNULL)
