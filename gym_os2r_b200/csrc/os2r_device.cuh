@@ -29,6 +29,12 @@
 
 #include "../../include/os2r.h"
 
+// A/B switch for the phase barriers of the physics loop (bit 0: loop top, bit 1: after the forward pass, bit 2: in front
+// of the contact rows) for tools/kprobe.py with a variant library (OS2R_LIB). The product build keeps all three.
+#ifndef OS2R_SKIP_PHASE_BARRIERS
+#define OS2R_SKIP_PHASE_BARRIERS 0
+#endif
+
 namespace os2r {
 
 // ------------------------------------------------------------------------------------------------
@@ -633,7 +639,7 @@ __device__ __forceinline__ void physics_iteration(const ModelDev<typename VT<V>:
             }
         }
     }
-    __syncthreads();   // second phase-alignment point per iteration (see the note at the physics loop)
+    if (!(OS2R_SKIP_PHASE_BARRIERS & 2)) __syncthreads();   // second phase-alignment point per iteration (see the note at the physics loop)
     // ---- Cholesky of M (and of M + dt*D when any joint is damped); qdd; v* = v + dt*qdd ------------------
     V L[N][N];       // Cholesky factor of the plain M (lower); Ld = reciprocal diagonal
     V Ld[N];
@@ -731,7 +737,7 @@ __device__ __forceinline__ void physics_iteration(const ModelDev<typename VT<V>:
         for (int k = r; k < N; ++k) z[k] += Gj[r][k] * l;
         C(SL::LAM + r) = l;
     }
-    __syncthreads();   // third phase-alignment point: the contact phase starts together (88.2 -> 87.4 us per step)
+    if (!(OS2R_SKIP_PHASE_BARRIERS & 4)) __syncthreads();   // third phase-alignment point: the contact phase starts together (88.2 -> 87.4 us per step)
     V Gc[NC][3][N];
     V Ac[NC][3];
     V bc[NC][3];     // row velocity before impulses, minus the target (penetration correction)

@@ -324,7 +324,7 @@ step_kernel(const __grid_constant__ ModelDev<typename VT<V>::S> M, const __grid_
     for (int s = 0; s < M.substeps; ++s) {
         // Keep the block's warps in phase: all warps of an SM run the same ~40 KB loop body, and warps that drift
         // apart thrash the instruction caches.
-        __syncthreads();
+        if (!(OS2R_SKIP_PHASE_BARRIERS & 1)) __syncthreads();
         physics_iteration<V, N, NC, DAMPED, SJ, SC, Cold<V, BLOCK>>(M, E, C);
     }
 #ifdef OS2R_CHECKED
