@@ -36,7 +36,7 @@ class Model(C.Structure):
     _fields_ = [
         ('n_dof', _i32), ('n_contacts', _i32), ('substeps', _i32), ('pgs_iters', _i32),
         ('axis', _i32 * MAX_DOF), ('role_dof', _i32 * N_ROLES),
-        ('contact_body', _i32 * MAX_CONTACTS), ('_pad0', _i32),
+        ('contact_body', _i32 * MAX_CONTACTS), ('pgs_joint_sweeps', _i32),
         ('tree_R', (_f64 * 9) * MAX_DOF), ('tree_p', (_f64 * 3) * MAX_DOF),
         ('mass', _f64 * MAX_DOF), ('com', (_f64 * 3) * MAX_DOF),
         ('inertia', (_f64 * 6) * MAX_DOF),

@@ -105,6 +105,7 @@ void build_model_dev(const os2r_model &m, const os2r_tuning &tune, ModelDev<T> &
     d.knee_dof = m.role_dof[OS2R_ROLE_KNEE];
     d.substeps = m.substeps;
     d.pgs_iters = m.pgs_iters;
+    d.pgs_joint_sweeps = m.pgs_joint_sweeps;
     d.pgs_tol2 = (T)(m.pgs_tol * m.pgs_tol);
     // lane-sorting hint: a proxy within this clearance may touch down during the next env step
     d.sort_margin = (T)(tune.sort_margin > 0.0 ? tune.sort_margin : 0.002);
@@ -382,6 +383,7 @@ int32_t os2r_create_tuned(const os2r_model *model, const os2r_task_cfg *task, in
         return fail("os2r_create: no kernel is built for %d moving joints with %d contact proxies (built: 2..5 joints with 3 proxies, 5 joints with 4)", model->n_dof, model->n_contacts);
     if (precision != 32 && precision != 64) return fail("os2r_create: precision must be 32 or 64");
     if (!(model->pgs_tol >= 0.0)) return fail("os2r_create: pgs_tol must be >= 0");
+    if (model->pgs_joint_sweeps < 0) return fail("os2r_create: pgs_joint_sweeps must be >= 0");
     if (task->obs_dim <= 0 || task->obs_dim > OS2R_MAX_OBS) return fail("os2r_create: obs_dim %d out of range", task->obs_dim);
     if (task->n_resets <= 0 || task->n_resets > OS2R_MAX_RESETS) return fail("os2r_create: n_resets %d out of range", task->n_resets);
     if (model->role_dof[OS2R_ROLE_HIP] < 0 || model->role_dof[OS2R_ROLE_KNEE] < 0) return fail("os2r_create: model lacks hip/knee joints");

@@ -59,6 +59,7 @@ struct ModelDev {
     int32_t contact_body[OS2R_MAX_CONTACTS];
     int32_t hip_dof, knee_dof;
     int32_t substeps, pgs_iters;
+    int32_t pgs_joint_sweeps;    // sweeps of an iteration that include the joint-friction rows (0: all)
     int32_t any_damping;         // 0 when every joint's nominal damping is 0 (skip 2nd factorisation)
     int32_t root_spin;           // 1: body 0 hangs off the world and turns about an axis parallel to gravity (the yaw
                                  //    pivot). Its whole contribution to the dynamics is then a CONSTANT added to M[0][0]
@@ -821,6 +822,7 @@ __device__ __forceinline__ void physics_iteration(const ModelDev<typename VT<V>:
         V zs[N];
 #pragma unroll
         for (int k = 0; k < N; ++k) zs[k] = z[k];
+        if (M.pgs_joint_sweeps <= 0 || it < M.pgs_joint_sweeps)   // os2r_model.pgs_joint_sweeps (warp-uniform)
 #pragma unroll
         for (int r = 0; r < N; ++r) {
             // branch-free: a row without friction has bound 0, so its impulse stays 0 and the update adds 0

@@ -172,6 +172,7 @@ def compile_urdf(path: str, physics: dict, max_torque=(2.5, 2.5)) -> CompiledMod
     m.substeps = int(physics.get('substeps', 10))
     m.pgs_iters = int(physics['pgs_iters'])
     m.pgs_tol = float(physics.get('pgs_tol', 0.0))
+    m.pgs_joint_sweeps = int(physics.get('pgs_joint_sweeps', 1))
     m.gravity_z = float(physics['gravity_z'])
     m.dt = float(physics['dt'])
     m.erp = float(physics['erp'])

@@ -74,7 +74,10 @@ typedef struct os2r_model {
     int32_t axis[OS2R_MAX_DOF];       /* joint axis in the child frame: 0=x 1=y 2=z              */
     int32_t role_dof[OS2R_N_ROLES];   /* chain index of hip/knee/pitch/yaw/boom_connector or -1  */
     int32_t contact_body[OS2R_MAX_CONTACTS];
-    int32_t _pad0;
+    int32_t pgs_joint_sweeps;         /* the joint-friction rows are relaxed in the first pgs_joint_sweeps sweeps of a
+                                         physics iteration only, the contact rows in every sweep (default 1: their
+                                         impulses are bounded by friction*dt ~ 1e-6 N m s and warm-started, the sweeps
+                                         after the first iterate on the contacts); 0: in every sweep              */
     double tree_R[OS2R_MAX_DOF][9];   /* row-major; parent coords = R * child coords at q = 0    */
     double tree_p[OS2R_MAX_DOF][3];   /* joint origin in the parent (moving body or world) frame */
     double mass[OS2R_MAX_DOF];

@@ -318,7 +318,8 @@ static void pgs_sweeps(const os2r_model *M, const env_params *P, const constrain
     for (it = 0; it < sweeps; ) {
         double v0[NMAX], dlam[RMAX] = {0};
         for (int i = 0; i < n; ++i) v0[i] = v[i];
-        for (int r = 0; r < S->n_rows; ++r) {
+        /* the joint-friction rows take part in the first pgs_joint_sweeps sweeps only (os2r_model.pgs_joint_sweeps) */
+        for (int r = (M->pgs_joint_sweeps > 0 && it >= M->pgs_joint_sweeps) ? n : 0; r < S->n_rows; ++r) {
             if (!S->active[r]) continue;
             double lo, hi;
             if (r < n) { hi = P->friction[r] * M->dt; lo = -hi; }

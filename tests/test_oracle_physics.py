@@ -141,12 +141,14 @@ def test_fixed_sweeps_track_converged_lcp():
     rng = np.random.RandomState(5)
     acts = 0.1 * rng.uniform(-1, 1, (120, 2))
 
-    def roll(sweeps, tol):
+    def roll(sweeps, tol, joint_sweeps=1):
+        m.pgs_joint_sweeps = joint_sweeps
         q, v, lam = q0.copy(), np.zeros(n), np.zeros(n + 9)
         for a in acts:
             q, v, lam = oracle.substeps(m, p, q, v, lam, a, 10, sweeps=sweeps, tol=tol)
         return q
-    ref = roll(4000, 1e-16)
+    ref = roll(4000, 1e-16, joint_sweeps=0)             # every row in every sweep, to convergence
+    assert np.abs(roll(8, 0.0, joint_sweeps=0) - ref).max() < 2e-3
     assert np.abs(roll(8, 0.0) - ref).max() < 2e-3      # ~30 steps after touchdown
     assert np.abs(roll(8, 0.0) - ref).max() < np.abs(roll(2, 0.0) - ref).max()
 
@@ -188,12 +190,13 @@ def test_sweep_tolerance_rule():
     q0[cm.dof_of('planarizer_pitch_joint')], q0[cm.dof_of('hip_joint')], q0[cm.dof_of('knee_joint')] = 0.15, 0.2861, -0.5877
     acts = 0.1 * np.random.RandomState(5).uniform(-1, 1, (120, 2))
 
-    def roll(sweeps, tol):
+    def roll(sweeps, tol, joint_sweeps=1):
+        m.pgs_joint_sweeps = joint_sweeps
         q, v, lam = q0.copy(), np.zeros(n), np.zeros(n + 9)
         for a in acts:
             q, v, lam = oracle.substeps(m, p, q, v, lam, a, 10, sweeps=sweeps, tol=tol)
         return q
-    ref = roll(4000, 1e-16)
+    ref = roll(4000, 1e-16, joint_sweeps=0)             # every row in every sweep, to convergence
     sweeps_done()
     e_fixed = np.abs(roll(8, 0.0) - ref).max()
     total_fixed, iters = sweeps_done()
@@ -215,7 +218,7 @@ def test_converged_sweeps_solve_the_boxed_lcp():
     answers exactly) with matrices rebuilt here in numpy — w = J (v* + Minv J^T lam) - target + cfm A_rr lam_r must be
     >= 0 where lam sits on its lower bound, <= 0 on its upper bound, and 0 in between; bounds: joint friction
     +-f dt, normal [0, inf), tangents +-mu lam_n."""
-    task, cm, cfg = make_config('fixed_hip', reward='BalancingV1')
+    task, cm, cfg = make_config('fixed_hip', reward='BalancingV1', pgs_joint_sweeps=0)   # every row in every sweep
     m, n, nc = cm.struct, cm.n_dof, cm.struct.n_contacts
     p = oracle.nominal_params(m)
     p[2 * n:3 * n] = [0.02, 0.03, 0.015, 0.04]          # joint friction N m
