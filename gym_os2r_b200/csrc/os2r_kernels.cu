@@ -493,14 +493,14 @@ struct StepFn {          // one instantiation of the step kernel
 
 // Structure signatures of the shipped models (gym_os2r_b200/models/assets/*.urdf), as model_signature() computes
 // them: monopod-simple (2 joints), monopod-fixed (3), monopod-fixed_hip (4), monopod (5, with and without the bracket
-// proxy). tests/test_capi_cpu.py::test_shipped_models_run_the_specialised_kernels keeps the table honest; any other
-// model runs the all-general instantiation.
-template <int N, int NC> struct Shipped { static constexpr uint32_t J = 0xffffffffu, C = 0xffffffffu; };   // none
-template <> struct Shipped<2, 3> { static constexpr uint32_t J = OS2R_SHIPPED_J23, C = OS2R_SHIPPED_C23; };
-template <> struct Shipped<3, 3> { static constexpr uint32_t J = OS2R_SHIPPED_J33, C = OS2R_SHIPPED_C33; };
-template <> struct Shipped<4, 3> { static constexpr uint32_t J = OS2R_SHIPPED_J43, C = OS2R_SHIPPED_C43; };
-template <> struct Shipped<5, 3> { static constexpr uint32_t J = OS2R_SHIPPED_J53, C = OS2R_SHIPPED_C53; };
-template <> struct Shipped<5, 4> { static constexpr uint32_t J = OS2R_SHIPPED_J54, C = OS2R_SHIPPED_C54; };
+// proxy), and whether that model's joints are damped. tests/test_capi_cpu.py::test_shipped_models_run_the_specialised_kernels
+// keeps the table honest; any other model runs the all-general instantiation.
+template <int N, int NC> struct Shipped { static constexpr uint32_t J = 0xffffffffu, C = 0xffffffffu; static constexpr bool DAMPED = false; };   // none
+template <> struct Shipped<2, 3> { static constexpr uint32_t J = OS2R_SHIPPED_J23, C = OS2R_SHIPPED_C23; static constexpr bool DAMPED = true; };
+template <> struct Shipped<3, 3> { static constexpr uint32_t J = OS2R_SHIPPED_J33, C = OS2R_SHIPPED_C33; static constexpr bool DAMPED = true; };
+template <> struct Shipped<4, 3> { static constexpr uint32_t J = OS2R_SHIPPED_J43, C = OS2R_SHIPPED_C43; static constexpr bool DAMPED = false; };
+template <> struct Shipped<5, 3> { static constexpr uint32_t J = OS2R_SHIPPED_J53, C = OS2R_SHIPPED_C53; static constexpr bool DAMPED = true; };
+template <> struct Shipped<5, 4> { static constexpr uint32_t J = OS2R_SHIPPED_J54, C = OS2R_SHIPPED_C54; static constexpr bool DAMPED = true; };
 
 template <typename V, int N, int NC, int BLOCK, bool DAMPED, bool SPECIAL>
 StepFn step_fn() {
@@ -512,14 +512,16 @@ StepFn step_fn() {
 }
 template <typename V, int N, int NC, int BLOCK>
 StepFn step_fn_d(bool damped, uint32_t sj, uint32_t sc) {
-    // the shipped models are undamped: the specialised kernels exist for the builds those models run
+    // the specialised fp32 kernels exist for the damping variant the shipped model of this shape runs (Shipped::DAMPED:
+    // monopod-fixed_hip carries no joint damping, the other URDFs do); the fp64 verification build keeps one (damped)
+    // instantiation per signature — with zero damping its second factor equals the first
     const bool special = sj == Shipped<N, NC>::J && sc == Shipped<N, NC>::C;
-    // the fp64 verification build keeps one (damped) instantiation; with zero damping its second factor equals the first
     if constexpr (sizeof(typename VT<V>::S) == 8) {
         return special ? step_fn<V, N, NC, BLOCK, true, true>() : step_fn<V, N, NC, BLOCK, true, false>();
     } else {
-        if (damped) return step_fn<V, N, NC, BLOCK, true, false>();
-        return special ? step_fn<V, N, NC, BLOCK, false, true>() : step_fn<V, N, NC, BLOCK, false, false>();
+        constexpr bool SD = Shipped<N, NC>::DAMPED;
+        if (special && damped == SD) return step_fn<V, N, NC, BLOCK, SD, true>();
+        return damped ? step_fn<V, N, NC, BLOCK, true, false>() : step_fn<V, N, NC, BLOCK, false, false>();
     }
 }
 template <typename V>
