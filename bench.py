@@ -415,7 +415,7 @@ def main():
         hbm_peak = peaks.get('hbm_gbs', 6650.0)
         # DRAM traffic per launch of the step kernel from the committed `ncu --set full` capture of this workload
         # (dram__bytes_read.sum + dram__bytes_write.sum), else null.
-        traffic, traffic_file = None, {3: 'r2_step_kernel_steady.txt', 4: 'r2_step_kernel_free_hip_steady.txt'}.get(args.config)
+        traffic, traffic_file = None, {3: 'r2b_step_kernel_steady.txt', 4: 'r2b_step_kernel_free_hip_steady.txt'}.get(args.config)
         try:
             tot = 0.0
             unit_scale = {'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}
@@ -423,7 +423,7 @@ def main():
                 if ln.startswith('dram__bytes_read.sum') or ln.startswith('dram__bytes_write.sum'):
                     _, val, unit = ln.split()
                     tot += float(val) * unit_scale[unit]
-            traffic = (tot * N / C['envs']) or None       # the capture was taken at the config's own batch size
+            traffic = (tot * N / 65536) or None           # tools/profile_step.py captures 65 536 envs: scaled to this batch
         except Exception:
             pass
         nominal_peak = 148 * 128 * 2 * 1.965e9 / 1e12

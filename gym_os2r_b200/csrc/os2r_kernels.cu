@@ -505,7 +505,7 @@ template <> struct Shipped<5, 4> { static constexpr uint32_t J = OS2R_SHIPPED_J5
 template <typename V, int N, int NC, int BLOCK, bool DAMPED, bool SPECIAL>
 StepFn step_fn() {
     // two resident 7-warp blocks per SM for the float build (128 registers per thread); everything else: no occupancy target
-    constexpr int MINB = (VT<V>::LANES == 1 && sizeof(typename VT<V>::S) == 4 && BLOCK == OS2R_BLOCK_WIDE) ? 2 : 1;
+    constexpr int MINB = (VT<V>::LANES == 1 && sizeof(typename VT<V>::S) == 4 && BLOCK == OS2R_BLOCK_WIDE) ? OS2R_WIDE_MINB : 1;
     constexpr uint32_t SJ = SPECIAL ? Shipped<N, NC>::J : generic_joint_signature(N);
     constexpr uint32_t SC = SPECIAL ? Shipped<N, NC>::C : generic_contact_signature(NC);
     return StepFn{(const void *)step_kernel<V, N, NC, BLOCK, DAMPED, MINB, SJ, SC>, step_smem_bytes<V, N, NC, BLOCK>(), BLOCK * VT<V>::LANES};

@@ -12,6 +12,9 @@
 #ifndef OS2R_BLOCK_WIDE
 #define OS2R_BLOCK_WIDE 224
 #endif
+#ifndef OS2R_WIDE_MINB
+#define OS2R_WIDE_MINB 2     // resident wide blocks per SM the build targets (A/B: 448-thread blocks, one per SM)
+#endif
 
 // Structure signatures (os2r_device.cuh) of the shipped URDFs, as os2r_model_signature reports them.
 #define OS2R_SHIPPED_J23 0x40000ab8u
