@@ -325,8 +325,36 @@ __device__ inline double rng_uniform(uint64_t seed, uint64_t env_id, uint32_t ep
     uint32_t a = (k & 1) ? x[2] : x[0], b = (k & 1) ? x[3] : x[1];
     return ((double)(a >> 5) * 67108864.0 + (double)(b >> 6)) * (1.0 / 9007199254740992.0);
 }
+// both uniforms of one Philox block: draws 2*block and 2*block + 1
+__device__ inline void rng_uniform_pair(uint64_t seed, uint64_t env_id, uint32_t episode, uint32_t block, double *u0, double *u1) {
+    uint32_t x[4];
+    philox4x32(seed, env_id, episode, block, x);
+    *u0 = ((double)(x[0] >> 5) * 67108864.0 + (double)(x[1] >> 6)) * (1.0 / 9007199254740992.0);
+    *u1 = ((double)(x[2] >> 5) * 67108864.0 + (double)(x[3] >> 6)) * (1.0 / 9007199254740992.0);
+}
 __device__ inline void rng_normal2(uint64_t seed, uint64_t env_id, uint32_t episode, uint32_t k, double z[2]) {
     double u1 = rng_uniform(seed, env_id, episode, k), u2 = rng_uniform(seed, env_id, episode, k + 1);
+    double r = sqrt(-2.0 * log(1.0 - u1));
+    double s, c;
+    sincos(6.283185307179586476925 * u2, &s, &c);
+    z[0] = r * c; z[1] = r * s;
+}
+// Where the uniforms of a reset come from: straight from Philox (one block per call: the thread-per-env reset kernel), or
+// from a table the lanes of a warp filled together (the step kernel's in-kernel reset: lane L evaluates block L, so the
+// warp runs ONE Philox evaluation instead of the ~28 a reset consumes one after the other on its critical path).
+#define OS2R_N_DRAW_BLOCKS 21    /* draws 0 .. 41 (DRAW_GRAVITY + 1), two per Philox block */
+struct DrawsPhilox {
+    uint64_t seed, gid;
+    uint32_t ep;
+    __device__ double operator()(uint32_t k) const { return rng_uniform(seed, gid, ep, k); }
+};
+struct DrawsTable {
+    const double *u;             // [2 * OS2R_N_DRAW_BLOCKS]
+    __device__ double operator()(uint32_t k) const { return u[k]; }
+};
+template <typename D>
+__device__ inline void draw_normal2(const D &draw, uint32_t k, double z[2]) {   // same arithmetic as rng_normal2
+    double u1 = draw(k), u2 = draw(k + 1);
     double r = sqrt(-2.0 * log(1.0 - u1));
     double s, c;
     sincos(6.283185307179586476925 * u2, &s, &c);
@@ -1022,16 +1050,16 @@ __device__ inline void leg_joint_angles(const os2r_task_cfg &C, double bp, doubl
 }
 
 // per-env parameter draws for episode `ep` (randomizers/monopod.py:182-215); writes SoA params
-template <typename T>
-__device__ inline void draw_params(const TaskDev &K, StateDev<T> &S, int64_t e, uint64_t gid, uint32_t ep) {
+template <typename T, typename D>
+__device__ inline void draw_params(const TaskDev &K, StateDev<T> &S, int64_t e, uint32_t ep, const D &draw) {
     const os2r_task_cfg &C = K.cfg;
     const int64_t N = S.n_envs;
     for (int i = 0; i < K.n_dof; ++i) {
         double ms = 1.0, dm = K.nominal_damping[i], fr = K.nominal_friction[i];
         if (C.randomize_params) {
-            ms = C.mass_lo + (C.mass_hi - C.mass_lo) * rng_uniform(S.seed, gid, ep, DRAW_PARAMS + i);
-            fr = C.fric_lo + (C.fric_hi - C.fric_lo) * rng_uniform(S.seed, gid, ep, DRAW_PARAMS + OS2R_MAX_DOF + i);
-            dm = K.nominal_damping[i] * (C.damp_lo + (C.damp_hi - C.damp_lo) * rng_uniform(S.seed, gid, ep, DRAW_PARAMS + 2 * OS2R_MAX_DOF + i));
+            ms = C.mass_lo + (C.mass_hi - C.mass_lo) * draw(DRAW_PARAMS + i);
+            fr = C.fric_lo + (C.fric_hi - C.fric_lo) * draw(DRAW_PARAMS + OS2R_MAX_DOF + i);
+            dm = K.nominal_damping[i] * (C.damp_lo + (C.damp_hi - C.damp_lo) * draw(DRAW_PARAMS + 2 * OS2R_MAX_DOF + i));
         }
         S.mass_scale[i * N + e] = (T)ms;
         S.damping[i * N + e] = (T)dm;
@@ -1040,45 +1068,45 @@ __device__ inline void draw_params(const TaskDev &K, StateDev<T> &S, int64_t e, 
     for (int c = 0; c < K.n_contacts; ++c) {
         double mu = K.nominal_mu[c];
         if (C.randomize_params)
-            mu = C.mu_link * (C.mu_lo + (C.mu_hi - C.mu_lo) * rng_uniform(S.seed, gid, ep, DRAW_PARAMS + 3 * OS2R_MAX_DOF + c));
+            mu = C.mu_link * (C.mu_lo + (C.mu_hi - C.mu_lo) * draw(DRAW_PARAMS + 3 * OS2R_MAX_DOF + c));
         S.mu[c * N + e] = (T)mu;
     }
     // MonopodEnvRandomizer(num_physics_rollouts=K): randomize_physics again at every K-th reset of the env
     // (randomizers/monopod.py:36,56-61,371)
     if (C.randomize_gravity && C.gravity_redraw_resets > 0 && ep % (uint32_t)C.gravity_redraw_resets == 0) {
         double z[2];
-        rng_normal2(S.seed, gid, ep, DRAW_GRAVITY, z);
+        draw_normal2(draw, DRAW_GRAVITY, z);
         S.gravity_z[e] = (T)(C.grav_mean + C.grav_std * z[0]);
     }
 }
 
 // Reset pose draw (randomizers/monopod.py:67-135, monopod_no_rand.py:26-98). q[] in chain order.
-template <int N>
-__device__ inline int reset_pose(const TaskDev &K, uint64_t seed, uint64_t gid, uint32_t ep, double *q) {
+template <int N, typename D>
+__device__ inline int reset_pose(const TaskDev &K, const D &draw, double *q) {
     const os2r_task_cfg &C = K.cfg;
 #pragma unroll
     for (int i = 0; i < N; ++i) q[i] = 0;
-    int idx = (int)(rng_uniform(seed, gid, ep, DRAW_RESET) * C.n_resets);
+    int idx = (int)(draw(DRAW_RESET) * C.n_resets);
     if (idx >= C.n_resets) idx = C.n_resets - 1;
     double pitch = C.reset_pitch[idx];
     double leg[2];
     double yaw = 0;
     if (C.reset_randomized) {
-        pitch *= 0.8 + 0.4 * rng_uniform(seed, gid, ep, DRAW_PITCH);
+        pitch *= 0.8 + 0.4 * draw(DRAW_PITCH);
         double zz[2];
-        rng_normal2(seed, gid, ep, DRAW_NOISE, zz);
+        draw_normal2(draw, DRAW_NOISE, zz);
         const double r0 = fabs(0.2 * zz[0]), r1 = fabs(0.2 * zz[1]);
         const double rmax = r0 > r1 ? r0 : r1, rmin = r0 > r1 ? r1 : r0;
         if (!C.reset_laying[idx]) leg_joint_angles(C, pitch, leg);
-        else { leg[0] = 1.57 - (rng_uniform(seed, gid, ep, DRAW_LAYSIDE) < 0.5 ? 3.14 : 0.0); leg[1] = 0; }
+        else { leg[0] = 1.57 - (draw(DRAW_LAYSIDE) < 0.5 ? 3.14 : 0.0); leg[1] = 0; }
         leg[0] = leg[0] + (leg[0] > 0 ? 1.0 : 0.0) * rmax;   // (a>0 - a<0) == (a>0): reference precedence quirk
         leg[1] = leg[1] - (leg[1] > 0 ? 1.0 : 0.0) * rmin;
-        const double dir = 1.0 - (rng_uniform(seed, gid, ep, DRAW_DIR) < 0.5 ? 2.0 : 0.0);
+        const double dir = 1.0 - (draw(DRAW_DIR) < 0.5 ? 2.0 : 0.0);
         leg[0] *= dir; leg[1] *= dir;
-        yaw = -0.2 + 0.4 * rng_uniform(seed, gid, ep, DRAW_YAW);
+        yaw = -0.2 + 0.4 * draw(DRAW_YAW);
     } else if (C.simple_sample_reset) {
-        leg[0] = C.simple_lo[0] + (C.simple_hi[0] - C.simple_lo[0]) * rng_uniform(seed, gid, ep, DRAW_SIMPLE_HIP);
-        leg[1] = C.simple_lo[1] + (C.simple_hi[1] - C.simple_lo[1]) * rng_uniform(seed, gid, ep, DRAW_SIMPLE_KNEE);
+        leg[0] = C.simple_lo[0] + (C.simple_hi[0] - C.simple_lo[0]) * draw(DRAW_SIMPLE_HIP);
+        leg[1] = C.simple_lo[1] + (C.simple_hi[1] - C.simple_lo[1]) * draw(DRAW_SIMPLE_KNEE);
     } else {
         if (!C.reset_laying[idx]) leg_joint_angles(C, pitch, leg);
         else { leg[0] = 1.57; leg[1] = 0; }

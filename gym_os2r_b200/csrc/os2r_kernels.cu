@@ -21,15 +21,14 @@ __device__ unsigned long long g_check[8];
 // ------------------------------------------------------------------------------------------------
 // reset of one env, written straight to the SoA state (rare path, fp64 draws shared with the oracle)
 // ------------------------------------------------------------------------------------------------
-template <typename T, int N, int NC>
+// `draw(k)` yields the k-th uniform of episode `ep` of this env (os2r_device.cuh: DrawsPhilox / DrawsTable).
+template <typename T, int N, int NC, typename D>
 __device__ __noinline__ int reset_env_global(const TaskDev &K, StateDev<T> &S, int64_t e, const double *a_old,
-                                             float *obs_row) {
+                                             float *obs_row, uint32_t ep, const D &draw) {
     const int64_t NE = S.n_envs;
-    const uint64_t gid = (uint64_t)(S.first_env_id + e);
-    const uint32_t ep = S.episode[e] + 1u;
     S.episode[e] = ep;
     double q[N], v[N];
-    const int idx = reset_pose<N>(K, S.seed, gid, ep, q);
+    const int idx = reset_pose<N>(K, draw, q);
 #pragma unroll
     for (int i = 0; i < N; ++i) {
         v[i] = 0.0;
@@ -45,7 +44,7 @@ __device__ __noinline__ int reset_env_global(const TaskDev &K, StateDev<T> &S, i
     S.steps[e] = 0;
     S.ret[e] = 0.0;
     S.cls[e] = 0xFF;   // sorting hint unknown after a reset: treat every proxy as near the ground
-    draw_params<T>(K, S, e, gid, ep);
+    draw_params<T>(K, S, e, ep, draw);
     if (obs_row) {
         // the observation sees the state the device will actually integrate (hi+lo rounding of q)
         double qs[N];
@@ -65,7 +64,8 @@ __global__ void __launch_bounds__(OS2R_BLOCK) reset_kernel(const __grid_constant
     if (e >= S.n_envs) return;
     if (mask && !mask[e]) return;
     const double a_old[2] = {(double)S.a_prev[e], (double)S.a_prev[S.n_envs + e]};
-    reset_env_global<T, N, NC>(K, S, e, a_old, obs ? obs + e * K.cfg.obs_dim : nullptr);
+    const DrawsPhilox draw{S.seed, (uint64_t)(S.first_env_id + e), S.episode[e] + 1u};
+    reset_env_global<T, N, NC>(K, S, e, a_old, obs ? obs + e * K.cfg.obs_dim : nullptr, draw.ep, draw);
 }
 
 // nominal parameters + the once-per-env gravity draw (GazeboEnvRandomizer.__init__ -> randomize_physics)
@@ -334,6 +334,11 @@ step_kernel(const __grid_constant__ ModelDev<typename VT<V>::S> M, const __grid_
     //      thread is finished from shared memory, one after the other, by the same (rolled) code
 #pragma unroll
     for (int i = 0; i < N; ++i) { C(SL::QHI + i) = E.q_hi[i]; C(SL::VHI + i) = E.v[i]; }
+    // what the warp-cooperative reset below needs from the per-env part (one env per thread: LANES == 1)
+    bool do_reset = false, finished_ok = false;
+    int64_t en_r = 0;
+    int reset_idx_r = 0, cause_r = 0;
+    double a_old_r[2] = {0.0, 0.0};
 #pragma unroll 1
     for (int h = 0; h < LANES; ++h) {
         const bool ok = LANES == 1 ? valid[0] : (h ? valid[LANES - 1] : valid[0]);
@@ -392,7 +397,7 @@ step_kernel(const __grid_constant__ ModelDev<typename VT<V>::S> M, const __grid_
             atomicAdd(&stats->sum_length, (double)steps);
         }
         if (cause && (K.cfg.auto_reset || !finite)) {
-            reset_idx = reset_env_global<T, N, NC>(K, S, en, a_old, obs + en * D);   // also marks the env "unknown" (all near)
+            do_reset = true;     // done by the whole warp after this loop
         } else {
             // next step's sorting hint: which proxies ended within sort_margin of the ground
             unsigned cls = 0;
@@ -413,11 +418,45 @@ step_kernel(const __grid_constant__ ModelDev<typename VT<V>::S> M, const __grid_
             S.ret[en] = ret;
             for (int k = 0; k < D; ++k) obs[en * D + k] = (float)o[k];
         }
-        if (info) {
-            info[2 * en] = reset_idx;
-            info[2 * en + 1] = cause;
+        finished_ok = true; en_r = en; reset_idx_r = reset_idx; cause_r = cause; a_old_r[0] = a_old[0]; a_old_r[1] = a_old[1];
+    }
+    // ---- in-kernel resets, warp-cooperative. A reset consumes ~28 uniforms = 21 Philox4x32-10 blocks; evaluated one
+    //      after the other by the one lane whose env finished they were ~3 000 instructions at the very end of that
+    //      warp's life, i.e. on the kernel's critical path whenever ANY env of the batch finishes (free_hip / HoppingV1:
+    //      40 envs per step; measured 10 of 127 us per step). Here lane L evaluates block L for the finishing env and
+    //      the owner collects the 42 uniforms by shuffle: same stream, same values, one Philox evaluation deep.
+    {
+        const unsigned lane = threadIdx.x & 31u;
+        unsigned need = __ballot_sync(0xffffffffu, do_reset);
+        while (need) {
+            const int src = __ffs(need) - 1;
+            need &= need - 1u;
+            const uint64_t gid_mine = (uint64_t)(S.first_env_id + en_r);
+            const uint32_t ep_mine = (do_reset && (int)lane == src) ? S.episode[en_r] + 1u : 0u;
+            const uint32_t gid_lo = __shfl_sync(0xffffffffu, (uint32_t)gid_mine, src);
+            const uint32_t gid_hi = __shfl_sync(0xffffffffu, (uint32_t)(gid_mine >> 32), src);
+            const uint32_t ep = __shfl_sync(0xffffffffu, ep_mine, src);
+            const uint64_t gid = ((uint64_t)gid_hi << 32) | gid_lo;
+            double u0 = 0.0, u1 = 0.0;
+            if (lane < OS2R_N_DRAW_BLOCKS) rng_uniform_pair(S.seed, gid, ep, lane, &u0, &u1);
+            double table[2 * OS2R_N_DRAW_BLOCKS];
+#pragma unroll
+            for (int k = 0; k < OS2R_N_DRAW_BLOCKS; ++k) {
+                table[2 * k] = __shfl_sync(0xffffffffu, u0, k);
+                table[2 * k + 1] = __shfl_sync(0xffffffffu, u1, k);
+            }
+            if ((int)lane == src) {
+                const DrawsTable draw{table};
+                reset_idx_r = reset_env_global<T, N, NC>(K, S, en_r, a_old_r, obs + en_r * K.cfg.obs_dim, ep, draw);   // also marks the env "unknown" (all near)
+            }
         }
-        if (IO.reset_id8) IO.reset_id8[en] = (uint8_t)reset_idx;
+    }
+    if (finished_ok) {
+        if (info) {
+            info[2 * en_r] = reset_idx_r;
+            info[2 * en_r + 1] = cause_r;
+        }
+        if (IO.reset_id8) IO.reset_id8[en_r] = (uint8_t)reset_idx_r;
     }
 }
 
