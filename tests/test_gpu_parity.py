@@ -98,6 +98,37 @@ def test_single_step_parity(mode, contact):
         eng.close()
 
 
+def test_joint_sweep_rule_variants_match_the_oracle():
+    """os2r_model.pgs_joint_sweeps: the joint-friction rows take part in the first K sweeps of an iteration only (default
+    1), the contact rows in all of them; 0 = every sweep (the rule before round 2b). Kernel and oracle read the same field:
+    fp64 parity to rounding for K = 0, 1, 2 on states with pressed proxies, and the rule really changes the result."""
+    N = 256
+    rng = np.random.RandomState(53)
+    finals = {}
+    for K in (0, 1, 2):
+        task, cm, cfg, eng, orc = _pair('fixed_hip', N, 64, pgs_joint_sweeps=K)
+        assert cm.struct.pgs_joint_sweeps == K
+        n = cm.n_dof
+        if K == 0:
+            st = _random_state(cm, N, rng, True)
+            a = rng.uniform(-1, 1, (N, 2)).astype(np.float32)
+        params = eng.get_params()
+        params[:, 2 * n:3 * n] = 0.05                       # joint friction large enough for the rule to matter
+        eng.set_params(params); orc.params[:] = params
+        eng.set_state(st)
+        orc.state[:] = eng.get_state()
+        for _ in range(2):
+            eng.step(torch.as_tensor(a, device='cuda'))
+            orc.step(a.astype(np.float64))
+        eq, ev = _err(eng, orc, n)
+        assert eq < 1e-10 and ev < 1e-7, (K, eq, ev)       # random deep penetrations, velocities up to ~100 rad/s
+        assert (orc.state[:, 3 * n:3 * n + 9:3] > 0).sum() > 10
+        finals[K] = eng.get_state()[:, :2 * n].copy()
+        eng.close()
+    assert np.abs(finals[0] - finals[1]).max() > 1e-9       # different rules, different iterates ...
+    assert np.abs(finals[0] - finals[1])[:, :n].max() < 1e-3   # ... of the same physics
+
+
 def test_damping_written_through_set_params_is_implicit():
     """fixed_hip carries no joint damping, so its step kernel is the instantiation without the second (implicit
     damping) factorisation; a damping written through os2r_set_params must switch to the damped one and match the
