@@ -196,6 +196,12 @@ step_kernel(const __grid_constant__ ModelDev<typename VT<V>::S> M, const __grid_
     // block only) sort last and shadow the last env instead of exiting, so that the block-wide barriers inside the
     // physics loop stay legal; they are skipped by the epilogue, before anything is written.
     const int64_t window = (int64_t)blockIdx.x * EPB;
+    // Narrow blocks (two warps; batches of at most one wave of them) do not sort: such a batch is latency-bound — a step
+    // lasts as long as the slowest warp — so regrouping lanes saves nothing there, while the class byte's DRAM round trip
+    // and the sort's barriers sit in front of every other load of the launch.
+    constexpr bool SORT = OS2R_SORT_NARROW || BLOCK > 64;
+    int src[LANES];
+    if constexpr (SORT) {
     int key[LANES];
 #pragma unroll
     for (int h = 0; h < LANES; ++h) {
@@ -220,8 +226,11 @@ step_kernel(const __grid_constant__ ModelDev<typename VT<V>::S> M, const __grid_
             pf(S.ret + en); pf(reinterpret_cast<const float2 *>(IO.actions) + en);
         }
     }
-    int src[LANES];
     sorted_sources<BLOCK, LANES, (1 << NC) + 1>(key, src, reinterpret_cast<int *>(smem_raw));
+    } else {
+#pragma unroll
+        for (int h = 0; h < LANES; ++h) src[h] = h * BLOCK + threadIdx.x;
+    }
 #ifdef OS2R_CHECKED
     {   // the sort must hand every window slot to exactly one thread
         __shared__ int owner[EPB];

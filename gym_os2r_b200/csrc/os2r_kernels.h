@@ -12,6 +12,9 @@
 #ifndef OS2R_BLOCK_WIDE
 #define OS2R_BLOCK_WIDE 224
 #endif
+#ifndef OS2R_SORT_NARROW
+#define OS2R_SORT_NARROW 0    // 1: the 64-thread blocks run the lane sort too (A/B: 2-4 % slower at every narrow-block batch size)
+#endif
 #ifndef OS2R_WIDE_MINB
 #define OS2R_WIDE_MINB 2     // resident wide blocks per SM the build targets (A/B: 448-thread blocks, one per SM)
 #endif
