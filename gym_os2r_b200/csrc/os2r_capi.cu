@@ -108,7 +108,7 @@ void build_model_dev(const os2r_model &m, const os2r_tuning &tune, ModelDev<T> &
     d.pgs_joint_sweeps = m.pgs_joint_sweeps;
     d.pgs_tol2 = (T)(m.pgs_tol * m.pgs_tol);
     // lane-sorting hint: a proxy within this clearance may touch down during the next env step
-    d.sort_margin = (T)(tune.sort_margin > 0.0 ? tune.sort_margin : 0.002);
+    d.sort_margin = (T)(tune.sort_margin > 0.0 ? tune.sort_margin : 0.001);   // tools/exp_sort_margin.py: 0.05 .. 1 mm 74.1 us, 2 mm 75.6, 8 mm 77.1
     // Root body turning about an axis parallel to gravity (z): its contribution to the joint-space dynamics is the
     // constant inertia about that axis (see ModelDev::root_spin). Axis of joint 0 in the world = first column of the
     // normalised tree_R[0]; the tilt tolerance (1e-9 rad) is far below the fp32 kernel's own rounding

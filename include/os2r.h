@@ -172,7 +172,7 @@ int32_t os2r_create(const os2r_model *model, const os2r_task_cfg *task, int64_t 
  * Zero-initialise for the defaults. */
 typedef struct os2r_tuning {
     double sort_margin;        /* ground clearance (m) below which a contact proxy counts as "near" for the lane sort;
-                                  <= 0: default 0.002                                                              */
+                                  <= 0: default 0.001                                                              */
     int32_t force_block;       /* threads per block of the step kernel (64, or 224 for the fp32 builds); 0: chosen
                                   from the batch size                                                             */
     int32_t disable_specialisation; /* 1: run the all-general step kernel even when the model has the structure of a
