@@ -111,6 +111,10 @@ struct StepIO {
     int32_t *term_count;         // [1], zeroed by the caller before the launch
     int32_t *term_records;       // [term_cap][D + 2] words
     int32_t term_cap;
+    // envs [env_begin, env_end) of the batch are stepped by this launch (env_end == 0: all of them). The packed host step
+    // launches the two halves of a large batch one after the other so that the first half's device-to-host copy runs under
+    // the second half's kernel (os2r_capi.cu).
+    int64_t env_begin, env_end;
 };
 
 struct StatsDev {                // device-side accumulators (os2r_stats without env_steps)

@@ -178,7 +178,8 @@ typedef struct os2r_tuning {
     int32_t disable_specialisation; /* 1: run the all-general step kernel even when the model has the structure of a
                                   shipped URDF (verification of the specialised kernels)                          */
     int32_t disable_root_fold; /* 1: run the general per-body code for the yaw pivot (verification of the fold)  */
-    int32_t _pad;
+    int32_t disable_host_split; /* 1: os2r_step_host_packed steps a large batch in ONE launch + ONE device-to-host copy
+                                  (default: two half-batch launches, the first half's copy under the second's kernel)  */
 } os2r_tuning;
 /* os2r_create with explicit tuning (NULL = defaults = os2r_create). */
 int32_t os2r_create_tuned(const os2r_model *model, const os2r_task_cfg *task, int64_t n_envs,
