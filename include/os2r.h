@@ -239,7 +239,9 @@ typedef struct os2r_packed_layout {
 int32_t os2r_packed_layout_get(const os2r_env *env, int32_t prefix_records, os2r_packed_layout *out);
 /* actions[N,2] (host) -> block (host, laid out as above; page-locked memory is written by DMA directly, pageable
  * memory through the handle's staging block). *n_terminal = number of finished envs; when it exceeds
- * prefix_records the remaining records are fetched with os2r_fetch_terminal_records before the next step. */
+ * prefix_records the remaining records are fetched with os2r_fetch_terminal_records before the next step.
+ * Batches of >= 131 072 envs are stepped as two half-batch launches, the first half's observations copied down while the
+ * second half is stepped (os2r_tuning.disable_host_split = 1: one launch, one copy); the block's contents are the same. */
 int32_t os2r_step_host_packed(os2r_env *env, const float *actions, void *block, int32_t prefix_records,
                               int32_t *n_terminal);
 /* The same step in two halves, for VecEnv.step_async / step_wait (subproc_vec_env.py:114-123: send the actions, do
