@@ -129,10 +129,12 @@ struct StatsDev {                // device-side accumulators (os2r_stats without
 //                    instructions of sm_100 (PTX fma/add/sub/mul.rn.f32x2 -> SASS FFMA2 / FADD2 / FMUL2). One FFMA2
 //                    issues in ONE scheduler slot and does the work of two FFMAs (measured on B200,
 //                    tools/microbench/ffma2_probe.cu: same 4.6-cycle dependent latency as FFMA, two FMA-pipe cycles per
-//                    warp instruction, i.e. the same peak flops through HALF the issue slots). The step kernel is
-//                    issue- and latency-bound, not FMA-pipe-bound, so the pair build is the
-//                    product path for fp32. Scalars (model constants in the constant bank, immediates) broadcast to both
-//                    halves inside the instruction (`R.F32` / `UR.F32` operand forms): no duplication needed.
+//                    warp instruction, i.e. the same peak flops through HALF the issue slots). Scalars (model constants
+//                    in the constant bank, immediates) broadcast to both halves inside the instruction (`R.F32` /
+//                    `UR.F32` operand forms): no duplication needed. MEASURED AND NOT SHIPPED: with one 7-warp block per
+//                    SM at 255 registers the pair build ran 106 us per step against 89 for one env per thread
+//                    (the kernel is bound by dependent-issue latency once 1.75 warps share a
+//                    scheduler); no kernel is instantiated on f2 any more, the type stays for the record and for A/B.
 // Per-half operations without a packed instruction (min / max / compare / select / MUFU) run once per half.
 // ------------------------------------------------------------------------------------------------
 struct f2 {
