@@ -195,8 +195,8 @@ step_kernel(const __grid_constant__ ModelDev<typename VT<V>::S> M, const __grid_
     // Thread t steps the envs at sorted positions LANES*t.. of the block's window. Slots past the end of the batch (last
     // block only) sort last and shadow the last env instead of exiting, so that the block-wide barriers inside the
     // physics loop stay legal; they are skipped by the epilogue, before anything is written.
-    const int64_t EB = IO.env_end > 0 ? IO.env_begin : 0, EE = IO.env_end > 0 ? IO.env_end : NE;   // this launch's envs
-    const int64_t window = EB + (int64_t)blockIdx.x * EPB;
+    const int64_t EE = IO.env_end;   // this launch steps envs [env_begin, env_end) (the launcher fills in the whole batch)
+    const int64_t window = IO.env_begin + (int64_t)blockIdx.x * EPB;
     // Narrow blocks (two warps; batches of at most one wave of them) do not sort: such a batch is latency-bound — a step
     // lasts as long as the slowest warp — so regrouping lanes saves nothing there, while the class byte's DRAM round trip
     // and the sort's barriers sit in front of every other load of the launch.
@@ -611,8 +611,11 @@ cudaError_t launch_step(int build, int n_dof, int n_contacts, int block, uint32_
     // blocks that need more than 48 KB of dynamic shared memory were opted in by prepare_step (once per handle,
     // on the handle's device: the attribute is per device, a process can hold handles on several GPUs)
     void *args[] = {(void *)&M, (void *)&K, (void *)&S, (void *)&io, (void *)&stats};
-    const int64_t count = io.env_end > 0 ? io.env_end - io.env_begin : S.n_envs;
-    if (count <= 0 || io.env_begin < 0 || (io.env_end > 0 && io.env_end > S.n_envs)) return cudaErrorInvalidValue;
+    StepIO io_full = io;                         // env_end == 0: the whole batch
+    if (io_full.env_end <= 0) { io_full.env_begin = 0; io_full.env_end = S.n_envs; }
+    const int64_t count = io_full.env_end - io_full.env_begin;
+    if (count <= 0 || io_full.env_begin < 0 || io_full.env_end > S.n_envs) return cudaErrorInvalidValue;
+    args[3] = (void *)&io_full;
     return cudaLaunchKernel(f.fn, dim3(grid_for(count, f.envs_per_block)), dim3(block), args, f.smem, stream);
 }
 
