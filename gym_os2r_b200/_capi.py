@@ -74,7 +74,7 @@ class TaskCfg(C.Structure):
 class Tuning(C.Structure):
     """struct os2r_tuning (zero = defaults)"""
     _fields_ = [('sort_margin', _f64), ('force_block', _i32), ('disable_specialisation', _i32), ('disable_root_fold', _i32),
-                ('disable_host_split', _i32)]
+                ('_pad', _i32)]
 
 
 class PackedLayout(C.Structure):

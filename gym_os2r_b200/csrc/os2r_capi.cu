@@ -205,18 +205,9 @@ struct os2r_env {
     bool packed_pending = false, packed_block_pinned = false;   // a packed step enqueued by ..._begin, not yet completed
     void *packed_block = nullptr;
     int32_t packed_prefix = 0;
-    // split packed step (two launches over the halves of a large batch; see os2r_step_host_packed_begin)
-    cudaStream_t host_stream2 = nullptr;
-    cudaEvent_t ev_first_half = nullptr, ev_actions2 = nullptr;
-    int block_half = 0;              // block width of a half-batch launch (0: the batch is not split)
-    bool no_host_split = false;
     int64_t launches = 0;
     uint64_t env_steps = 0;
 };
-
-#ifndef OS2R_HOST_SPLIT_MIN_ENVS
-#define OS2R_HOST_SPLIT_MIN_ENVS 131072
-#endif
 
 namespace {
 
@@ -352,16 +343,15 @@ int set_params_impl(os2r_env *h, StateDev<T> &S, const double *in) {
            put_real(h, S.mu, nc, mu) || put_real(h, S.gravity_z, 1, gz);
 }
 
-int do_step(os2r_env *h, const StepIO &io, cudaStream_t stream, int block = 0) {
+int do_step(os2r_env *h, const StepIO &io, cudaStream_t stream) {
     cudaError_t e;
-    if (block == 0) block = h->block;
     if (h->precision == 32)
-        e = launch_step<float>(h->build, h->model.n_dof, h->model.n_contacts, block, h->sig_j, h->sig_c, h->m32, h->taskdev, h->s32, io, h->stats, stream);
+        e = launch_step<float>(h->build, h->model.n_dof, h->model.n_contacts, h->block, h->sig_j, h->sig_c, h->m32, h->taskdev, h->s32, io, h->stats, stream);
     else
-        e = launch_step<double>(h->build, h->model.n_dof, h->model.n_contacts, block, h->sig_j, h->sig_c, h->m64, h->taskdev, h->s64, io, h->stats, stream);
+        e = launch_step<double>(h->build, h->model.n_dof, h->model.n_contacts, h->block, h->sig_j, h->sig_c, h->m64, h->taskdev, h->s64, io, h->stats, stream);
     if (e != cudaSuccess) return fail("step kernel launch failed: %s", cudaGetErrorString(e));
     h->launches += 1;
-    h->env_steps += (uint64_t)(io.env_end > 0 ? io.env_end - io.env_begin : h->n);
+    h->env_steps += (uint64_t)h->n;
     return 0;
 }
 
@@ -451,17 +441,6 @@ int32_t os2r_create_tuned(const os2r_model *model, const os2r_task_cfg *task, in
     if ((e = cudaMemset(h->stats, 0, sizeof(StatsDev))) != cudaSuccess) return cleanup("cudaMemset(stats)", e);
     e = prepare_step(h->build, model->n_dof, model->n_contacts, h->block, h->sig_j, h->sig_c);
     if (e != cudaSuccess) return cleanup("cudaFuncSetAttribute(step kernel shared memory)", e);
-    // Very large batches are stepped in two halves by the packed host step (the first half's device-to-host copy runs
-    // under the second half's kernel). Only where a half still fills the GPU: two launches of 32 768 envs take 102 us of
-    // kernel time against 74 for one of 65 536, more than the overlap wins back (tools/exp_host_split.py).
-    h->no_host_split = tune.disable_host_split != 0;
-    if (!h->no_host_split && n_envs >= OS2R_HOST_SPLIT_MIN_ENVS) {
-        h->block_half = tune.force_block ? h->block : step_block_threads(h->build, n_envs / 2 + (n_envs & 1), sm_count);
-        if (h->block_half != h->block) {
-            e = prepare_step(h->build, model->n_dof, model->n_contacts, h->block_half, h->sig_j, h->sig_c);
-            if (e != cudaSuccess) return cleanup("cudaFuncSetAttribute(step kernel shared memory, half batch)", e);
-        }
-    }
     if (precision == 32) { carve<float>(h, h->s32); e = launch_init<float>(h->taskdev, h->s32, model->gravity_z, 0); }
     else { carve<double>(h, h->s64); e = launch_init<double>(h->taskdev, h->s64, model->gravity_z, 0); }
     if (e != cudaSuccess) return cleanup("init kernel", e);
@@ -484,9 +463,6 @@ int32_t os2r_destroy(os2r_env *h) {
         cudaFree(h->dev_done); cudaFree(h->dev_info);
         cudaFree(h->dev_block); cudaFreeHost(h->pin_block);
         if (h->host_stream) cudaStreamDestroy(h->host_stream);
-        if (h->host_stream2) { cudaStreamSynchronize(h->host_stream2); cudaStreamDestroy(h->host_stream2); }
-        if (h->ev_first_half) cudaEventDestroy(h->ev_first_half);
-        if (h->ev_actions2) cudaEventDestroy(h->ev_actions2);
     }
     delete h;
     return 0;
@@ -614,56 +590,7 @@ int32_t os2r_step_host_packed_begin(os2r_env *h, const float *actions, void *blo
         h->pin_block_bytes = (size_t)L.total_bytes;
     }
     if (!pa) memcpy(h->pin_actions, actions, N * 2 * sizeof(float));
-    const float *src_actions = pa ? actions : h->pin_actions;
-    unsigned char *dst = pb ? (unsigned char *)block : h->pin_block;
-    if (h->block_half) {
-        // ---- split step: the two halves of the batch are two launches. Stream 1: actions of half A up, kernel A, kernel B,
-        //      results of half B (+ the terminal records of both) down; stream 2: actions of half B up (under kernel A),
-        //      results of half A down (under kernel B). An env's result does not depend on which launch steps it
-        //      (tests: sharding invariance), so the caller sees exactly what the single launch produces; the copies per
-        //      field keep the block's layout (obs, reward, done, reset id stay contiguous [N, ...] arrays).
-        if (!h->host_stream2) {
-            CK(cudaStreamCreate(&h->host_stream2));
-            CK(cudaEventCreateWithFlags(&h->ev_first_half, cudaEventDisableTiming));
-            CK(cudaEventCreateWithFlags(&h->ev_actions2, cudaEventDisableTiming));
-        }
-        cudaStream_t st2 = h->host_stream2;
-        const int64_t NA = N / 2, NB = N - NA;
-        const int D = h->task.obs_dim;
-        CK(cudaMemcpyAsync(h->dev_actions, src_actions, NA * 2 * sizeof(float), cudaMemcpyHostToDevice, st));
-        CK(cudaMemcpyAsync(h->dev_actions + NA * 2, src_actions + NA * 2, NB * 2 * sizeof(float), cudaMemcpyHostToDevice, st2));
-        CK(cudaEventRecord(h->ev_actions2, st2));
-        CK(cudaMemsetAsync(h->dev_block + L.term_count, 0, 16, st));
-        StepIO io{};
-        io.actions = h->dev_actions;
-        io.obs = (float *)(h->dev_block + L.obs);
-        io.reward = (float *)(h->dev_block + L.reward);
-        io.done = h->dev_block + L.done;
-        io.reset_id8 = h->dev_block + L.reset_id;
-        io.term_count = (int32_t *)(h->dev_block + L.term_count);
-        io.term_records = (int32_t *)(h->dev_block + L.term_records);
-        io.term_cap = (int32_t)N;
-        // Three copies down: the observations of half A (the bulk of its bytes) under kernel B, then the observations of
-        // half B, then everything behind the observations — reward, done, reset id, record count, records, which are
-        // contiguous for the whole batch — in one piece. (A copy per field and half measured 211 us per step against 177
-        // for the single launch at 65 536 envs: nine small copies cost more than the overlap gains.)
-        io.env_begin = 0; io.env_end = NA;
-        if (do_step(h, io, st, h->block_half)) return 1;
-        CK(cudaEventRecord(h->ev_first_half, st));
-        CK(cudaStreamWaitEvent(st2, h->ev_first_half, 0));
-        CK(cudaMemcpyAsync(dst + L.obs, h->dev_block + L.obs, (size_t)NA * D * 4, cudaMemcpyDeviceToHost, st2));
-        CK(cudaStreamWaitEvent(st, h->ev_actions2, 0));
-        io.env_begin = NA; io.env_end = N;
-        if (do_step(h, io, st, h->block_half)) return 1;
-        CK(cudaMemcpyAsync(dst + L.obs + NA * D * 4, h->dev_block + L.obs + NA * D * 4, (size_t)NB * D * 4, cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(dst + L.reward, h->dev_block + L.reward, (size_t)(L.total_bytes - L.reward), cudaMemcpyDeviceToHost, st));
-        h->packed_pending = true;
-        h->packed_block = block;
-        h->packed_block_pinned = pb;
-        h->packed_prefix = prefix_records;
-        return 0;
-    }
-    CK(cudaMemcpyAsync(h->dev_actions, src_actions, N * 2 * sizeof(float), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(h->dev_actions, pa ? actions : h->pin_actions, N * 2 * sizeof(float), cudaMemcpyHostToDevice, st));
     CK(cudaMemsetAsync(h->dev_block + L.term_count, 0, 16, st));
     StepIO io{};
     io.actions = h->dev_actions;
@@ -675,6 +602,7 @@ int32_t os2r_step_host_packed_begin(os2r_env *h, const float *actions, void *blo
     io.term_records = (int32_t *)(h->dev_block + L.term_records);
     io.term_cap = (int32_t)N;
     if (do_step(h, io, st)) return 1;
+    unsigned char *dst = pb ? (unsigned char *)block : h->pin_block;
     CK(cudaMemcpyAsync(dst, h->dev_block, (size_t)L.total_bytes, cudaMemcpyDeviceToHost, st));
     h->packed_pending = true;
     h->packed_block = block;
@@ -691,7 +619,6 @@ int32_t os2r_step_host_packed_end(os2r_env *h, int32_t *n_terminal) {
     packed_layout(h, h->packed_prefix, &L);
     h->packed_pending = false;
     CK(cudaStreamSynchronize(h->host_stream));
-    if (h->block_half && h->host_stream2) CK(cudaStreamSynchronize(h->host_stream2));
     if (!h->packed_block_pinned) memcpy(h->packed_block, h->pin_block, (size_t)L.total_bytes);
     if (n_terminal) *n_terminal = *(const int32_t *)((const unsigned char *)h->packed_block + L.term_count);
     return 0;

@@ -31,18 +31,6 @@
 
 // A/B switch for the phase barriers of the physics loop (bit 0: loop top, bit 1: after the forward pass, bit 2: in front
 // of the contact rows) for tools/kprobe.py with a variant library (OS2R_LIB). The product build keeps all three.
-// code placement of the contact rows: 0 = hip sphere inline, the rarely pressed proxies out of line (default),
-// 1 = every proxy out of line, 2 = every proxy inline (A/B)
-#ifndef OS2R_PROXY_LAYOUT
-#define OS2R_PROXY_LAYOUT 0
-#endif
-#if OS2R_PROXY_LAYOUT == 1
-#define OS2R_PROXY_HINT(c, NC, a) __builtin_expect((a), 0)
-#elif OS2R_PROXY_LAYOUT == 2
-#define OS2R_PROXY_HINT(c, NC, a) (a)
-#else
-#define OS2R_PROXY_HINT(c, NC, a) (((c) == (NC) - 3) ? (a) : __builtin_expect((a), 0))
-#endif
 #ifndef OS2R_SKIP_PHASE_BARRIERS
 #define OS2R_SKIP_PHASE_BARRIERS 0
 #endif
@@ -123,10 +111,6 @@ struct StepIO {
     int32_t *term_count;         // [1], zeroed by the caller before the launch
     int32_t *term_records;       // [term_cap][D + 2] words
     int32_t term_cap;
-    // envs [env_begin, env_end) of the batch are stepped by this launch (env_end == 0: all of them). The packed host step
-    // launches the two halves of a large batch one after the other so that the first half's device-to-host copy runs under
-    // the second half's kernel (os2r_capi.cu).
-    int64_t env_begin, env_end;
 };
 
 struct StatsDev {                // device-side accumulators (os2r_stats without env_steps)
@@ -798,7 +782,7 @@ __device__ __forceinline__ void physics_iteration(const ModelDev<typename VT<V>:
         // every proxy but the hip sphere (index NC - 3 in the shipped models) presses in < 6 % of the envs: their rows are
         // marked unlikely so that ptxas lays them out behind the loop body (the hot path stays contiguous for the
         // instruction cache) — placement only, the arithmetic is the same
-        if (OS2R_PROXY_HINT(c, NC, act[c])) {
+        if ((c == NC - 3) ? act[c] : __builtin_expect(act[c], 0)) {
             const V bounce = fmin_t(depth * M.erp_over_dt, V(M.max_erv));
             const V x[3] = {C(SL::CX + 3 * c), C(SL::CX + 3 * c + 1), cz - M.contact_radius[c]};   // lowest point
             V J[3][N];   // rows: normal (z), tangent x, tangent y
@@ -886,7 +870,7 @@ __device__ __forceinline__ void physics_iteration(const ModelDev<typename VT<V>:
         }
 #pragma unroll
         for (int c = 0; c < NC; ++c) {
-            if (OS2R_PROXY_HINT(c, NC, act[c])) {
+            if ((c == NC - 3) ? act[c] : __builtin_expect(act[c], 0)) {
                 V ln = C(SL::LAM + N + 3 * c);
 #pragma unroll
                 for (int d = 0; d < 3; ++d) {

@@ -195,8 +195,7 @@ step_kernel(const __grid_constant__ ModelDev<typename VT<V>::S> M, const __grid_
     // Thread t steps the envs at sorted positions LANES*t.. of the block's window. Slots past the end of the batch (last
     // block only) sort last and shadow the last env instead of exiting, so that the block-wide barriers inside the
     // physics loop stay legal; they are skipped by the epilogue, before anything is written.
-    const int64_t EE = IO.env_end;   // this launch steps envs [env_begin, env_end) (the launcher fills in the whole batch)
-    const int64_t window = IO.env_begin + (int64_t)blockIdx.x * EPB;
+    const int64_t window = (int64_t)blockIdx.x * EPB;
     // Narrow blocks (two warps; batches of at most one wave of them) do not sort: such a batch is latency-bound — a step
     // lasts as long as the slowest warp — so regrouping lanes saves nothing there, while the class byte's DRAM round trip
     // and the sort's barriers sit in front of every other load of the launch.
@@ -207,7 +206,7 @@ step_kernel(const __grid_constant__ ModelDev<typename VT<V>::S> M, const __grid_
 #pragma unroll
     for (int h = 0; h < LANES; ++h) {
         const int64_t en = window + h * BLOCK + threadIdx.x;
-        const bool nominal_valid = en < EE;
+        const bool nominal_valid = en < NE;
         key[h] = nominal_valid ? 1 + (int)(__ldcg(S.cls + en) & ((1u << NC) - 1u)) : 0;
         // While the class byte travels and the block sorts, pull the window's state lines towards the L2: which env a
         // thread will step is not known yet, but it is one of this window's, so the DRAM latency of the prologue loads
@@ -252,8 +251,8 @@ step_kernel(const __grid_constant__ ModelDev<typename VT<V>::S> M, const __grid_
 #pragma unroll
     for (int h = 0; h < LANES; ++h) {
         const int64_t e_raw = window + src[h];
-        valid[h] = e_raw < EE;
-        e[h] = valid[h] ? e_raw : EE - 1;
+        valid[h] = e_raw < NE;
+        e[h] = valid[h] ? e_raw : NE - 1;
         OS2R_CHECK(e[h] >= 0 && e[h] < NE, 2);
     }
     const Cold<V, BLOCK> C{reinterpret_cast<V *>(smem_raw) + threadIdx.x};
@@ -611,12 +610,7 @@ cudaError_t launch_step(int build, int n_dof, int n_contacts, int block, uint32_
     // blocks that need more than 48 KB of dynamic shared memory were opted in by prepare_step (once per handle,
     // on the handle's device: the attribute is per device, a process can hold handles on several GPUs)
     void *args[] = {(void *)&M, (void *)&K, (void *)&S, (void *)&io, (void *)&stats};
-    StepIO io_full = io;                         // env_end == 0: the whole batch
-    if (io_full.env_end <= 0) { io_full.env_begin = 0; io_full.env_end = S.n_envs; }
-    const int64_t count = io_full.env_end - io_full.env_begin;
-    if (count <= 0 || io_full.env_begin < 0 || io_full.env_end > S.n_envs) return cudaErrorInvalidValue;
-    args[3] = (void *)&io_full;
-    return cudaLaunchKernel(f.fn, dim3(grid_for(count, f.envs_per_block)), dim3(block), args, f.smem, stream);
+    return cudaLaunchKernel(f.fn, dim3(grid_for(S.n_envs, f.envs_per_block)), dim3(block), args, f.smem, stream);
 }
 
 template <typename T>

@@ -178,8 +178,7 @@ typedef struct os2r_tuning {
     int32_t disable_specialisation; /* 1: run the all-general step kernel even when the model has the structure of a
                                   shipped URDF (verification of the specialised kernels)                          */
     int32_t disable_root_fold; /* 1: run the general per-body code for the yaw pivot (verification of the fold)  */
-    int32_t disable_host_split; /* 1: os2r_step_host_packed steps a large batch in ONE launch + ONE device-to-host copy
-                                  (default: two half-batch launches, the first half's copy under the second's kernel)  */
+    int32_t _pad;
 } os2r_tuning;
 /* os2r_create with explicit tuning (NULL = defaults = os2r_create). */
 int32_t os2r_create_tuned(const os2r_model *model, const os2r_task_cfg *task, int64_t n_envs,
@@ -239,9 +238,7 @@ typedef struct os2r_packed_layout {
 int32_t os2r_packed_layout_get(const os2r_env *env, int32_t prefix_records, os2r_packed_layout *out);
 /* actions[N,2] (host) -> block (host, laid out as above; page-locked memory is written by DMA directly, pageable
  * memory through the handle's staging block). *n_terminal = number of finished envs; when it exceeds
- * prefix_records the remaining records are fetched with os2r_fetch_terminal_records before the next step.
- * Batches of >= 131 072 envs are stepped as two half-batch launches, the first half's observations copied down while the
- * second half is stepped (os2r_tuning.disable_host_split = 1: one launch, one copy); the block's contents are the same. */
+ * prefix_records the remaining records are fetched with os2r_fetch_terminal_records before the next step. */
 int32_t os2r_step_host_packed(os2r_env *env, const float *actions, void *block, int32_t prefix_records,
                               int32_t *n_terminal);
 /* The same step in two halves, for VecEnv.step_async / step_wait (subproc_vec_env.py:114-123: send the actions, do

@@ -605,44 +605,6 @@ def test_packed_host_step_matches_device_step():
         e1.close(); e2.close()
 
 
-def test_split_packed_host_step_matches_single_launch():
-    """From 131 072 envs on, os2r_step_host_packed steps the batch as two half-batch launches (the first half's
-    device-to-host copy runs under the second half's kernel). What the caller sees must be exactly what the single launch
-    (os2r_tuning.disable_host_split, and the device-buffer step) produces: observations, rewards, done flags, reset ids,
-    the set of terminal records, and the state afterwards — on an odd batch size, with TimeLimit resets in both halves."""
-    N = 131072 + 37
-    task, cm, cfg = make_config('fixed_hip', reward='BalancingV2', auto_reset=True, max_episode_steps=4,
-                                reset_randomized=True, randomize_params=True, reset_positions=('stand', 'lay', 'ground'))
-    e_dev = Engine(cm, cfg, N, seed=4)
-    e_one = Engine(cm, cfg, N, seed=4, tuning={'disable_host_split': 1})
-    e_two = Engine(cm, cfg, N, seed=4)
-    for e in (e_dev, e_one, e_two):
-        e.reset()
-    rng = np.random.RandomState(3)
-    finished = 0
-    for t in range(9):
-        a = rng.uniform(-1, 1, (N, 2)).astype(np.float32)
-        o0, r0, d0, i0 = e_dev.step(torch.as_tensor(a, device='cuda'))
-        o0, r0, d0, i0 = o0.cpu().numpy(), r0.cpu().numpy(), d0.cpu().numpy().astype(bool), i0.cpu().numpy()
-        l1, l2 = e_one.kernel_launches, e_two.kernel_launches
-        out1 = e_one.step_host_packed(a, prefix_records=N)
-        out2 = e_two.step_host_packed(a, prefix_records=N)
-        assert e_one.kernel_launches - l1 == 1 and e_two.kernel_launches - l2 == 2
-        for out in (out1, out2):
-            o, r, d, rid, t_idx, t_cause, t_obs = out
-            np.testing.assert_array_equal(o, o0); np.testing.assert_array_equal(r, r0)
-            assert np.array_equal(d, d0) and np.array_equal(rid, i0[:, 0])
-            order = np.argsort(t_idx)
-            assert np.array_equal(t_idx[order], np.flatnonzero(d0))
-            assert np.array_equal(t_cause[order], i0[d0, 1])
-            np.testing.assert_array_equal(t_obs[order], e_dev.terminal_obs.cpu().numpy()[d0])
-        finished += int(d0.sum())
-    assert finished == 2 * N
-    assert np.array_equal(e_dev.get_state(), e_one.get_state()) and np.array_equal(e_dev.get_state(), e_two.get_state())
-    for e in (e_dev, e_one, e_two):
-        e.close()
-
-
 def test_energy_conservation_on_device():
     """Size-independent property: with damping = friction = 0, no torque, no contact, the semi-implicit
     integrator keeps total mechanical energy within O(dt) of its initial value over 500 env steps."""
