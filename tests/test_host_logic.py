@@ -284,3 +284,13 @@ def test_randomizer_wrapper_forwards_num_physics_rollouts():
     with pytest.raises(ValueError):
         randomizers.monopod.MonopodEnvRandomizer(env=functools.partial(make_env_from_id, env_id='Monopod-balance-v1'),
                                                  num_physics_rollouts=-1)
+
+
+def test_solver_constants_reach_the_model_struct():
+    """The backend's own solver constants (settings.yaml `physics:`) are forwarded into os2r_model, and the per-runtime
+    overrides of configure() win: sweep cap, per-env exit tolerance, sweeps that include the joint-friction rows."""
+    from helpers import make_config
+    task, cm, cfg = make_config('fixed_hip', pgs_tol=None)
+    assert cm.struct.pgs_iters == 8 and cm.struct.pgs_tol == 1e-6 and cm.struct.pgs_joint_sweeps == 1
+    task, cm, cfg = make_config('fixed_hip', pgs_iters=5, pgs_tol=0.0, pgs_joint_sweeps=0)
+    assert cm.struct.pgs_iters == 5 and cm.struct.pgs_tol == 0.0 and cm.struct.pgs_joint_sweeps == 0
