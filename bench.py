@@ -236,6 +236,15 @@ def main():
 
     fp32_peak, _ = measure_fp32_peak(local_rank)
 
+    def head_start():
+        # After a synchronize the launch queue is empty: the GPU reaches a step's first event record as soon as the
+        # host issues it and then WAITS for the step kernel's launch to arrive, so the host's launch path (torch.rand,
+        # ctypes, ~60 us) was billed to the first two event pairs of every timed window (108 and 92 us against 78:
+        # OS2R_BENCH_TRACE=1). A few untimed flushes in front give the host its lead before the first pair instead
+        # of after the second; the timed quantity stays the sum of the K per-step event pairs.
+        for _ in range(8):
+            flush.zero_()
+
     policy = graph = static_obs = None
     if args.config == 5:
         torch.manual_seed(7)
@@ -282,6 +291,7 @@ def main():
     ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
     sampler.start()
     wall0 = time.perf_counter()
+    head_start()
     if args.config == 5:
         for i in range(K):
             flush.zero_()
@@ -303,11 +313,15 @@ def main():
         dist.barrier()
     per_step_ms = [a.elapsed_time(b) for a, b in zip(ev0, ev1)]
     total_ms = float(sum(per_step_ms))
+    if os.environ.get('OS2R_BENCH_TRACE'):        # diagnosis only: the per-step device times of the timed window
+        print('per_step_us', [round(x * 1e3, 1) for x in per_step_ms[:64]], file=sys.stderr)
     st = eng.stats()                               # timed window only
     contact1, any1 = contact_fractions(eng)
     # hot-L2 variant: K back-to-back steps, no flush (state stays resident in the 126 MB L2)
     s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     pool = [new_actions() for _ in range(min(K, 256))]
+    for i in range(4):                             # untimed: the host's launch lead (see head_start) and a warm L2
+        timed_step() if args.config == 5 else eng.step(pool[i % len(pool)])
     s0.record()
     if args.config == 5:
         for i in range(K):
@@ -376,6 +390,7 @@ def main():
             eng.step(new_actions())
         f0 = [torch.cuda.Event(enable_timing=True) for _ in range(50)]
         f1 = [torch.cuda.Event(enable_timing=True) for _ in range(50)]
+        head_start()
         for i in range(50):
             flush.zero_()
             a = new_actions()
