@@ -39,6 +39,7 @@ CONFIGS = {
             what='Monopod-hop-v1 (free_hip) + MonopodEnvRandomizer driven by a torch MLP policy 10-64-64-2 (tanh) on the '
                  'device, policy forward + fused env step captured in ONE CUDA graph'),
 }
+HEAD_START_FLUSHES = int(os.environ.get('OS2R_BENCH_HEAD', '32'))   # x 45 us of untimed GPU work in front of a timed window
 PREROLL_STEPS = 1000     # untimed: from the `stand` reset the first touchdown happens around env step 90 and the
                          # collapse / bounce transient (more sweeps per iteration than later) lasts a few hundred more
 
@@ -242,7 +243,7 @@ def main():
         # ctypes, ~60 us) was billed to the first two event pairs of every timed window (108 and 92 us against 78:
         # OS2R_BENCH_TRACE=1). A few untimed flushes in front give the host its lead before the first pair instead
         # of after the second; the timed quantity stays the sum of the K per-step event pairs.
-        for _ in range(8):
+        for _ in range(HEAD_START_FLUSHES):
             flush.zero_()
 
     policy = graph = static_obs = None
