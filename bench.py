@@ -378,7 +378,11 @@ def main():
         d2h = 4
         e2e_api = 'CUDA-graph replay (policy + step) + reward.mean().item() per step; observations never leave the device'
     te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    e2e_per_rank = [e2e_s / K2 * 1e3]
     if world > 1:
+        tl = [torch.zeros_like(te) for _ in range(world)]
+        dist.all_gather(tl, te)                       # per-rank figures travel with the line: ranks share the host's
+        e2e_per_rank = [round(float(x[0]) / K2 * 1e3, 5) for x in tl]   # PCIe root ports and memory bandwidth
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_s = float(te[0])
 
@@ -459,7 +463,8 @@ def main():
                             'parallelism': f'env-sharded x{world}, no data-path collective'},
                     clocks=sampler.result(),
                     e2e={'value': world * N * K2 / e2e_s, 'unit': 'env-steps/s', 'h2d_bytes_per_step': h2d,
-                         'd2h_bytes_per_step': d2h, 'steps': K2, 'ms_per_step': e2e_s / K2 * 1e3, 'api': e2e_api},
+                         'd2h_bytes_per_step': d2h, 'steps': K2, 'ms_per_step': e2e_s / K2 * 1e3, 'ms_per_step_per_rank': e2e_per_rank,
+                         'api': e2e_api},
                     gpu_launches=int(launches),
                     roofline={'bound': 'fp32', 'achieved': achieved_tf, 'peak': fp32_peak, 'unit': 'TFLOP/s',
                               'frac': achieved_tf / fp32_peak if fp32_peak else None, 'traffic': traffic,
